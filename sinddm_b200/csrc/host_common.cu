@@ -1,0 +1,99 @@
+// Error slot, device init and TMA descriptor encoding.
+#include "host_common.h"
+
+#include <cudaTypedefs.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace sinddm {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+const char* last_error() { return g_err; }
+
+static DeviceInfo g_dev = {0, -1, 0, 0};
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+
+const DeviceInfo& device_info() { return g_dev; }
+
+int init_device(int device) {
+    SINDDM_CUDA_OK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    SINDDM_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("sinddm_b200 is built for sm_100a only; device %d reports sm_%d%d", device, prop.major, prop.minor);
+        return SINDDM_ERR_INVALID;
+    }
+    if (!g_encode) {
+        // libcuda is resolved at run time through the runtime so the .so links without a driver present.
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        SINDDM_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || fn == nullptr) {
+            set_error("cuTensorMapEncodeTiled is not available from this driver");
+            return SINDDM_ERR_CUDA;
+        }
+        g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    }
+    g_dev.device = device;
+    g_dev.num_sms = prop.multiProcessorCount;
+    g_dev.max_smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
+    g_dev.initialized = 1;
+    return SINDDM_OK;
+}
+
+static int encode(CUtensorMap* out, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                  const cuuint32_t* box, CUtensorMapSwizzle swizzle) {
+    if (!g_encode) {
+        set_error("sinddm_init() must be called before any tensor-core entry point");
+        return SINDDM_ERR_NOT_INIT;
+    }
+    if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0) {
+        set_error("TMA base pointer %p is not 16-byte aligned", base);
+        return SINDDM_ERR_INVALID;
+    }
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
+                          dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu/%llu, box %u/%u)", (int)r, rank,
+                  (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+        return SINDDM_ERR_CUDA;
+    }
+    return SINDDM_OK;
+}
+
+int make_tmap_nhwc(CUtensorMap* out, const float* base, int B, int H, int W, int C, int box_c, int box_w, int box_h,
+                   CUtensorMapSwizzle swizzle) {
+    if ((C * 4) % 16 != 0) {
+        set_error("NHWC TMA descriptor needs C %% 4 == 0 (got C=%d)", C);
+        return SINDDM_ERR_INVALID;
+    }
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+    cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    return encode(out, base, 4, dims, strides, box, swizzle);
+}
+
+int make_tmap_2d(CUtensorMap* out, const float* base, int inner, int rows, int box_inner, int box_rows,
+                 CUtensorMapSwizzle swizzle) {
+    if ((inner * 4) % 16 != 0) {
+        set_error("2-D TMA descriptor needs inner %% 4 == 0 (got %d)", inner);
+        return SINDDM_ERR_INVALID;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)inner * 4};
+    cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows};
+    return encode(out, base, 2, dims, strides, box, swizzle);
+}
+
+}  // namespace sinddm

@@ -1,0 +1,124 @@
+// Internal operator interface between the network driver (net.cu / capi.cu) and the kernels.
+//
+// All activations inside the library are NHWC fp32 ([B,H,W,C], "P = B*H*W pixels x C channels"); only the
+// 3-channel boundary tensors (network input / output, diffusion state) are NCHW like the reference's.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "host_common.h"
+
+namespace sinddm {
+
+// ------------------------------------------------------------------------------------------------
+// Dense convolution as a GEMM:  out[p][n] = sum_{tap, c} in[p (+) tap][c] * w[tap][n][c]  (+ residual K-slices)
+//   ntaps = 9 (3x3, pad 1, tap = ky*3+kx, offset (ky-1, kx-1)) or 1 (1x1).
+// The same problem description drives the tcgen05 kernel (tc_conv.cu) and the fp32 CUDA-core kernel
+// (simt_conv.cu); forward convolutions and data-gradients differ only in how the weights were packed.
+// ------------------------------------------------------------------------------------------------
+struct ConvEpilogue {
+    const float* bias;      // [N] added to every pixel, or null
+    const float* res_add;   // [P,N] identity residual added before activation, or null
+    const float* x3;        // [P,3] NHWC: 1x1 residual conv from a 3-channel input ...
+    const float* w_res3;    // ... with weights [N,3]; both null when unused
+    int gelu;               // apply exact-erf GELU
+    float* out_pre;         // [P,N] pre-activation copy (saved for backward), or null
+    const float* dgelu_z;   // [P,N]: multiply result by gelu'(z) (data-gradient epilogue), or null
+    const float* w_final;   // [3,N] fused trailing 1x1 conv to 3 channels ...
+    const float* b_final;   // ... bias [3] ...
+    float* out_final;       // ... written NCHW [B,3,H,W]; all null when unused
+    int round_tf32;         // round `out` to tf32 (its only consumers are tensor-core operands)
+    float* out;             // [P,N], or null when only out_final is wanted
+};
+
+struct ConvProblem {
+    int B, H, W;
+    const float* in;      // [P,Cin]
+    int Cin;
+    const float* w;       // [ntaps][N][Cin]
+    int ntaps;
+    const float* in_res;  // [P,Cres] input of a fused 1x1 residual conv (extra K-slices), or null
+    int Cres;
+    const float* w_res;   // [N][Cres]
+    int N;
+    ConvEpilogue ep;
+};
+
+// tcgen05 path: needs Cin % 8 == 0, Cres % 8 == 0, N % 16 == 0, 16 <= N <= 160.
+struct TcConvOp {
+    CUtensorMap tm_a, tm_ares, tm_b, tm_bres;
+    ConvProblem p;
+    int stage_bytes, nstages, smem_bytes;
+    int tiles_w, tiles_h, ntiles, grid;
+};
+bool tc_conv_supported(const ConvProblem& p);
+int tc_conv_prepare(const ConvProblem& p, TcConvOp* op);
+int tc_conv_launch(const TcConvOp& op, cudaStream_t stream);
+
+int simt_conv_launch(const ConvProblem& p, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------------
+// Weight gradient:  partial[split][tap][ci][co] = sum_{p in split} x[p (+) tap][ci] * dy[p][co]
+// followed by a deterministic reduction over splits into the PyTorch parameter layout.
+// ------------------------------------------------------------------------------------------------
+struct WgradProblem {
+    int B, H, W;
+    const float* x;   // [P,Cx]
+    int Cx;
+    const float* dy;  // [P,Cy]
+    int Cy;
+    int ntaps;        // 9 or 1
+    float* partial;   // [nsplit][ntaps][Cx][Cy] scratch
+    int nsplit;       // chosen by *_plan
+};
+
+struct TcWgradOp {
+    CUtensorMap tm_x, tm_dy;
+    WgradProblem p;
+    int cxk, cyk, nchunks, tpc, ngroups, wt, nks, col_stride, tmem_cols;
+    int stage_bytes, nstages, smem_bytes;
+};
+bool tc_wgrad_supported(int Cx, int Cy);
+int tc_wgrad_nsplit(int B, int H, int W, int Cx, int Cy, int ntaps);
+int tc_wgrad_prepare(const WgradProblem& p, TcWgradOp* op);
+int tc_wgrad_launch(const TcWgradOp& op, cudaStream_t stream);
+
+int simt_wgrad_nsplit(int B, int H, int W, int Cx, int Cy, int ntaps);
+int simt_wgrad_launch(const WgradProblem& p, cudaStream_t stream);
+
+// dst (OIHW: [Cy][Cx][ntaps]) = sum_split partial;  transpose_out = 0 keeps [ntaps][Cx][Cy].
+int wgrad_reduce_launch(const float* partial, int nsplit, int ntaps, int Cx, int Cy, float* dst, int keep_layout,
+                        cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------------
+// Weight packing (PyTorch OIHW -> GEMM operand layouts), tf32-rounded when round != 0.
+//   fwd : dst[tap][co][ci] = w[co][ci][tap]
+//   dgrad: dst[tap][ci][co] = w[co][ci][ntaps-1-tap]
+// ------------------------------------------------------------------------------------------------
+int pack_conv_weights_launch(const float* w, int Cout, int Cin, int ntaps, float* dst_fwd, float* dst_dgrad, int round,
+                             cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------------
+// Depthwise 5x5 (pad 2):  out[p][c] = add[p][c] + bias[c] + cond[b][c] + sum_tap w[c][tap(') ] * in[p (+) tap][c]
+//   flip = 1 correlates with the flipped kernel (data gradient).
+// ------------------------------------------------------------------------------------------------
+int dw5x5_launch(const float* in, const float* w /*[C][25]*/, const float* bias, const float* cond /*[B][C]*/,
+                 const float* add, float* out, int B, int H, int W, int C, int flip, int round_tf32,
+                 cudaStream_t stream);
+
+// dW[c][tap] = sum_p x[p(+)tap][c] dh[p][c];  db[c] = sum_p dh[p][c];  dcond[b][c] = sum_hw dh[b,hw][c].
+// scratch needs dw5x5_wgrad_scratch_floats(B,H,C) floats.
+size_t dw5x5_wgrad_scratch_floats(int B, int H, int C);
+int dw5x5_wgrad_launch(const float* x, const float* dh, float* dw, float* db, float* dcond, float* scratch, int B,
+                       int H, int W, int C, cudaStream_t stream);
+
+// out[c] = sum_p a[p][c]; scratch needs colsum_scratch_floats(C) floats.
+size_t colsum_scratch_floats(int C);
+int colsum_launch(const float* a, long long P, int C, float* out, float* scratch, cudaStream_t stream);
+
+// 3-channel boundary layout changes.
+int nchw_to_nhwc_launch(const float* src, float* dst, int B, int C, int H, int W, cudaStream_t stream);
+int nhwc_to_nchw_launch(const float* src, float* dst, int B, int C, int H, int W, cudaStream_t stream);
+
+}  // namespace sinddm

@@ -1,0 +1,263 @@
+// fp32 CUDA-core versions of the dense convolution and its weight gradient.
+//
+// Two jobs: (1) the layers that are no dense contraction -- Cin = 3 (l1.net[0], l1.res_conv) and
+// Cout = 3 (final_conv, the data gradient into l1's depthwise output) -- which the tensor-core path does not
+// take (reference SinDDM/models.py:124,130-132); (2) `math = fp32` strict mode, in which EVERY convolution
+// runs here with plain FFMA so results can be checked against the CPU oracle at fp32 tolerance and the
+// tcgen05 kernels can be checked against an exact on-device twin.  Same ConvProblem / WgradProblem
+// contract as the tensor-core kernels, including every epilogue option.
+#include "common.cuh"
+#include "ops.h"
+
+namespace sinddm {
+
+namespace {
+
+constexpr int kTH = 8, kTW = 16;   // pixel tile, one pixel per thread
+constexpr int kNB = 32;            // output channels per pass (register accumulators)
+constexpr int kCK = 8;             // input channels per smem weight slab
+
+// weights slab in smem: ws[tap][ci (kCK)][kNB]  (co contiguous -> float4 broadcast reads)
+__global__ void __launch_bounds__(kTH* kTW)
+simt_conv_kernel(const ConvProblem p, int tiles_w, int tiles_h) {
+    __shared__ __align__(16) float ws[9 * kCK * kNB];
+
+    const int tile = blockIdx.x;
+    const int tw = tile % tiles_w;
+    const int th = (tile / tiles_w) % tiles_h;
+    const int b = tile / (tiles_w * tiles_h);
+    const int hl = threadIdx.x / kTW, wl = threadIdx.x % kTW;
+    const int h = th * kTH + hl, w = tw * kTW + wl;
+    const bool valid = (h < p.H) && (w < p.W);
+    const size_t pix = ((size_t)b * p.H + h) * p.W + w;
+    const ConvEpilogue& ep = p.ep;
+    const int N = p.N;
+
+    float x3v[3] = {0.f, 0.f, 0.f};
+    if (ep.x3 && valid) {
+        x3v[0] = ep.x3[pix * 3 + 0];
+        x3v[1] = ep.x3[pix * 3 + 1];
+        x3v[2] = ep.x3[pix * 3 + 2];
+    }
+    float fin[3] = {0.f, 0.f, 0.f};
+
+    // neighbour pixel base pointers (nullptr = zero padding)
+    for (int n0 = 0; n0 < N; n0 += kNB) {
+        float acc[kNB];
+#pragma unroll
+        for (int j = 0; j < kNB; ++j) acc[j] = 0.f;
+
+        // ---- main taps, then (phase 1) the optional 1x1 residual conv as extra K
+        for (int phase = 0; phase < 2; ++phase) {
+            const float* in = phase == 0 ? p.in : p.in_res;
+            const float* wt = phase == 0 ? p.w : p.w_res;
+            const int C = phase == 0 ? p.Cin : p.Cres;
+            const int ntaps = phase == 0 ? p.ntaps : 1;
+            if (in == nullptr) continue;
+            for (int c0 = 0; c0 < C; c0 += kCK) {
+                __syncthreads();
+                // stage weights: ws[tap][ci][j] = wt[tap][n0+j][c0+ci]
+                for (int i = threadIdx.x; i < ntaps * kCK * kNB; i += blockDim.x) {
+                    const int j = i % kNB;
+                    const int ci = (i / kNB) % kCK;
+                    const int tap = i / (kNB * kCK);
+                    const int n = n0 + j, c = c0 + ci;
+                    ws[i] = (n < N && c < C) ? wt[((size_t)tap * N + n) * C + c] : 0.f;
+                }
+                __syncthreads();
+                if (valid) {
+                    for (int tap = 0; tap < ntaps; ++tap) {
+                        int hh = h, ww = w;
+                        if (ntaps == 9) {
+                            hh += tap / 3 - 1;
+                            ww += tap % 3 - 1;
+                        }
+                        if (hh < 0 || hh >= p.H || ww < 0 || ww >= p.W) continue;
+                        const float* src = in + (((size_t)b * p.H + hh) * p.W + ww) * C + c0;
+                        const int cmax = min(kCK, C - c0);
+                        for (int ci = 0; ci < cmax; ++ci) {
+                            const float av = __ldg(src + ci);
+                            const float4* w4 = reinterpret_cast<const float4*>(&ws[(tap * kCK + ci) * kNB]);
+#pragma unroll
+                            for (int q = 0; q < kNB / 4; ++q) {
+                                const float4 wv = w4[q];
+                                acc[4 * q + 0] = fmaf(av, wv.x, acc[4 * q + 0]);
+                                acc[4 * q + 1] = fmaf(av, wv.y, acc[4 * q + 1]);
+                                acc[4 * q + 2] = fmaf(av, wv.z, acc[4 * q + 2]);
+                                acc[4 * q + 3] = fmaf(av, wv.w, acc[4 * q + 3]);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+
+        // ---- epilogue (identical semantics to the tensor-core kernel's)
+        if (valid) {
+#pragma unroll
+            for (int j = 0; j < kNB; ++j) {
+                const int n = n0 + j;
+                if (n < N) {
+                    float v = acc[j];
+                    if (ep.bias) v += ep.bias[n];
+                    if (ep.w_res3) {
+                        const float* wr = ep.w_res3 + n * 3;
+                        v = fmaf(x3v[2], wr[2], fmaf(x3v[1], wr[1], fmaf(x3v[0], wr[0], v)));
+                    }
+                    const size_t off = pix * N + n;
+                    if (ep.res_add) v += ep.res_add[off];
+                    if (ep.out_pre) ep.out_pre[off] = v;
+                    if (ep.gelu) v = gelu_erf(v);
+                    if (ep.dgelu_z) v *= gelu_erf_grad(ep.dgelu_z[off]);
+                    if (ep.w_final) {
+                        fin[0] = fmaf(v, ep.w_final[0 * N + n], fin[0]);
+                        fin[1] = fmaf(v, ep.w_final[1 * N + n], fin[1]);
+                        fin[2] = fmaf(v, ep.w_final[2 * N + n], fin[2]);
+                    }
+                    if (ep.out) ep.out[off] = ep.round_tf32 ? round_tf32(v) : v;
+                }
+            }
+        }
+    }
+
+    if (ep.w_final && valid) {
+        const size_t plane = (size_t)p.H * p.W;
+        float* o = ep.out_final + (size_t)b * 3 * plane + (size_t)h * p.W + w;
+        o[0] = fin[0] + (ep.b_final ? ep.b_final[0] : 0.f);
+        o[plane] = fin[1] + (ep.b_final ? ep.b_final[1] : 0.f);
+        o[2 * plane] = fin[2] + (ep.b_final ? ep.b_final[2] : 0.f);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// weight gradient, CUDA cores.  grid = (nsplit, ntaps, ceil(Cx/kCB)); thread <-> output channel co.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kCB = 8;
+constexpr int kPY = 4;   // pixel lanes per CTA (threadIdx.y), reduced through smem at the end
+
+__global__ void simt_wgrad_kernel(const WgradProblem p) {
+    extern __shared__ float red[];   // [kPY][kCB][blockDim.x]
+    const int split = blockIdx.x;
+    const int tap = blockIdx.y;
+    const int ci0 = blockIdx.z * kCB;
+    const int co = threadIdx.x;
+    const int py = threadIdx.y;
+    const long long P = (long long)p.B * p.H * p.W;
+    const long long p_begin = P * split / p.nsplit;
+    const long long p_end = P * (split + 1) / p.nsplit;
+    int dyo = 0, dxo = 0;
+    if (p.ntaps == 9) {
+        dyo = tap / 3 - 1;
+        dxo = tap % 3 - 1;
+    }
+    float acc[kCB];
+#pragma unroll
+    for (int i = 0; i < kCB; ++i) acc[i] = 0.f;
+    const int cmax = min(kCB, p.Cx - ci0);
+    const bool act = co < p.Cy;
+
+    for (long long q = p_begin + py; q < p_end; q += kPY) {
+        const int w = (int)(q % p.W);
+        const int h = (int)((q / p.W) % p.H);
+        const int hh = h + dyo, ww = w + dxo;
+        if (hh < 0 || hh >= p.H || ww < 0 || ww >= p.W || !act) continue;
+        const float* xs = p.x + (q + (long long)dyo * p.W + dxo) * p.Cx + ci0;
+        const float g = __ldg(p.dy + q * p.Cy + co);
+#pragma unroll
+        for (int i = 0; i < kCB; ++i)
+            if (i < cmax) acc[i] = fmaf(__ldg(xs + i), g, acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < kCB; ++i) red[(py * kCB + i) * blockDim.x + co] = acc[i];
+    __syncthreads();
+    if (py == 0 && act) {
+        for (int i = 0; i < cmax; ++i) {
+            float s = 0.f;
+#pragma unroll
+            for (int y = 0; y < kPY; ++y) s += red[(y * kCB + i) * blockDim.x + co];
+            p.partial[(((size_t)split * p.ntaps + tap) * p.Cx + ci0 + i) * p.Cy + co] = s;
+        }
+    }
+}
+
+// dst[co][ci][tap] (or [tap][ci][co] when keep_layout) = sum_s partial[s][tap][ci][co], fixed order.
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int nsplit, int ntaps, int Cx, int Cy,
+                                    float* __restrict__ dst, int keep_layout) {
+    const int total = ntaps * Cx * Cy;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    float s = 0.f;
+    for (int k = 0; k < nsplit; ++k) s += partial[(size_t)k * total + i];
+    if (keep_layout) {
+        dst[i] = s;
+    } else {
+        const int co = i % Cy;
+        const int ci = (i / Cy) % Cx;
+        const int tap = i / (Cy * Cx);
+        dst[((size_t)co * Cx + ci) * ntaps + tap] = s;
+    }
+}
+
+__global__ void pack_conv_weights_kernel(const float* __restrict__ w, int Cout, int Cin, int ntaps,
+                                         float* __restrict__ dst_fwd, float* __restrict__ dst_dgrad, int round) {
+    const int total = Cout * Cin * ntaps;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int tap = i % ntaps;
+    const int ci = (i / ntaps) % Cin;
+    const int co = i / (ntaps * Cin);
+    float v = w[i];
+    if (round) v = round_tf32(v);
+    if (dst_fwd) dst_fwd[((size_t)tap * Cout + co) * Cin + ci] = v;
+    if (dst_dgrad) dst_dgrad[((size_t)(ntaps - 1 - tap) * Cin + ci) * Cout + co] = v;
+}
+
+}  // namespace
+
+int simt_conv_launch(const ConvProblem& p, cudaStream_t stream) {
+    SINDDM_REQUIRE(p.ntaps == 9 || p.ntaps == 1, "simt_conv: ntaps must be 9 or 1");
+    SINDDM_REQUIRE(p.N >= 1 && p.Cin >= 1, "simt_conv: bad channel counts");
+    const int tiles_w = ceil_div(p.W, kTW), tiles_h = ceil_div(p.H, kTH);
+    const int ntiles = tiles_w * tiles_h * p.B;
+    simt_conv_kernel<<<ntiles, kTH * kTW, 0, stream>>>(p, tiles_w, tiles_h);
+    SINDDM_CUDA_OK(cudaGetLastError());
+    return SINDDM_OK;
+}
+
+int simt_wgrad_nsplit(int B, int H, int W, int Cx, int Cy, int ntaps) {
+    long long P = (long long)B * H * W;
+    long long n = P / 1024;
+    if (n < 1) n = 1;
+    if (n > 1024) n = 1024;
+    // keep the split-partial scratch of one layer under 64 MiB
+    while (n > 1 && n * ntaps * Cx * Cy * 4 > (64ll << 20)) n /= 2;
+    return (int)n;
+}
+
+int simt_wgrad_launch(const WgradProblem& p, cudaStream_t stream) {
+    dim3 grid(p.nsplit, p.ntaps, ceil_div(p.Cx, kCB));
+    const int tx = (int)align_up((size_t)p.Cy, 32);
+    SINDDM_REQUIRE(tx * kPY <= 1024, "simt_wgrad: Cy=%d too large", p.Cy);
+    dim3 block(tx, kPY);
+    simt_wgrad_kernel<<<grid, block, (size_t)kPY * kCB * tx * sizeof(float), stream>>>(p);
+    SINDDM_CUDA_OK(cudaGetLastError());
+    return SINDDM_OK;
+}
+
+int wgrad_reduce_launch(const float* partial, int nsplit, int ntaps, int Cx, int Cy, float* dst, int keep_layout,
+                        cudaStream_t stream) {
+    const int total = ntaps * Cx * Cy;
+    wgrad_reduce_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(partial, nsplit, ntaps, Cx, Cy, dst, keep_layout);
+    SINDDM_CUDA_OK(cudaGetLastError());
+    return SINDDM_OK;
+}
+
+int pack_conv_weights_launch(const float* w, int Cout, int Cin, int ntaps, float* dst_fwd, float* dst_dgrad, int round,
+                             cudaStream_t stream) {
+    const int total = Cout * Cin * ntaps;
+    pack_conv_weights_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(w, Cout, Cin, ntaps, dst_fwd, dst_dgrad, round);
+    SINDDM_CUDA_OK(cudaGetLastError());
+    return SINDDM_OK;
+}
+
+}  // namespace sinddm
