@@ -1,0 +1,120 @@
+"""Host-side helpers with the reference's names and semantics (reference: SinDDM/functions.py).
+
+Only the helpers on the hot path's boundary are here: small utilities, the cosine schedule, `extract`,
+`noise_like` and the pyramid builder `create_img_scales` (called by main.py before any model exists).
+Harmonization / CLIP / ROI helpers (dilate_mask, thresholded_grad, stat_from_bbs, extract_patch) are out of
+scope.
+"""
+from __future__ import annotations
+
+import inspect
+from pathlib import Path
+
+import numpy as np
+import torch
+from PIL import Image
+
+APEX_AVAILABLE = False  # the apex fp16 path is dead in the reference (fp16=False hard-coded, main.py:122)
+
+
+def exists(x):
+    """functions.py:72"""
+    return x is not None
+
+
+def default(val, d):
+    """functions.py:76 -- `d` may be a value or a zero-argument function."""
+    if val is not None:
+        return val
+    return d() if inspect.isfunction(d) else d
+
+
+def cycle(dl):
+    """functions.py:82 -- endless iteration over a data loader."""
+    while True:
+        yield from dl
+
+
+def num_to_groups(num, divisor):
+    """functions.py:88 -- [divisor, divisor, ..., remainder]."""
+    full, rem = divmod(num, divisor)
+    return [divisor] * full + ([rem] if rem > 0 else [])
+
+
+def loss_backwards(fp16, loss, optimizer, **kwargs):
+    """functions.py:97 -- the apex branch cannot be taken here (no apex, fp16 is always False)."""
+    if fp16:
+        raise RuntimeError("fp16/apex training is not supported (dead path in the reference)")
+    loss.backward(**kwargs)
+
+
+def extract(a, t, x_shape):
+    """functions.py:105 -- a[t] reshaped to broadcast over x_shape."""
+    picked = a.gather(-1, t)
+    return picked.reshape(t.shape[0], *([1] * (len(x_shape) - 1)))
+
+
+def noise_like(shape, device, repeat=False):
+    """functions.py:111 -- same torch.randn call shapes as the reference (RNG-stream parity, quirk Q7)."""
+    if repeat:
+        one = torch.randn((1, *shape[1:]), device=device)
+        return one.repeat(shape[0], *([1] * (len(shape) - 1)))
+    return torch.randn(shape, device=device)
+
+
+def cosine_beta_schedule(timesteps, s=0.008):
+    """functions.py:117 -- cosine schedule; keeps the reference's linspace(0, steps, steps) (quirk Q4)."""
+    steps = timesteps + 1
+    grid = np.linspace(0, steps, steps)
+    alpha_bar = np.cos(((grid / steps) + s) / (1 + s) * np.pi * 0.5) ** 2
+    alpha_bar = alpha_bar / alpha_bar[0]
+    betas = 1 - (alpha_bar[1:] / alpha_bar[:-1])
+    return np.clip(betas, a_min=0, a_max=0.999)
+
+
+def create_img_scales(foldername, filename, scale_factor=1.411, image_size=None, create=False, auto_scale=None):
+    """Pyramid builder, functions.py:130-192.
+
+    Returns (sizes [(W, H) per scale], rescale_losses, adjusted scale_factor, n_scales) and, with create=True,
+    writes <folder>/scale_i/<name>.png and <folder>/scale_i_recon/<name>.png.  Bit-compatible with the
+    reference, including the uint8 wrap-around in the rescale losses (quirk Q1: np.subtract on two PIL
+    images stays uint8).
+    """
+    source = Image.open(foldername + filename)
+    png_name = filename.rsplit(".", 1)[0] + ".png"
+    if image_size is None:
+        image_size = source.size
+    if auto_scale is not None:
+        shrink = np.sqrt((image_size[0] * image_size[1]) / auto_scale)
+        if shrink > 1:
+            image_size = (int(image_size[0] / shrink), int(image_size[1] / shrink))
+
+    # coarsest scale: area ~3110 px so the 35-px receptive field covers ~40 % of it, short side in [42, 55]
+    short, long_ = min(image_size), max(image_size)
+    coarse = int(round(np.sqrt(3110 * short / long_)))
+    coarse = min(max(coarse, 42), 55)
+    n_scales = int(round(np.log(short / coarse) / np.log(scale_factor)) + 1)
+    scale_factor = np.exp(np.log(short / coarse) / (n_scales - 1))
+
+    sizes, pyramid = [], []
+    for i in range(n_scales):
+        shrink = np.power(scale_factor, n_scales - i - 1)
+        size_i = (int(round(image_size[0] / shrink)), int(round(image_size[1] / shrink)))
+        level = source.resize(size_i, Image.LANCZOS)
+        if create:
+            out_dir = Path(foldername + "scale_" + str(i) + "/")
+            out_dir.mkdir(parents=True, exist_ok=True)
+            level.save(str(out_dir / png_name))
+        sizes.append(size_i)
+        pyramid.append(level)
+
+    rescale_losses = []
+    for i in range(n_scales - 1):
+        blurry = pyramid[i].resize(sizes[i + 1], Image.BILINEAR)
+        diff = np.subtract(pyramid[i + 1], blurry)          # uint8 arithmetic, wraps (Q1)
+        rescale_losses.append(np.linalg.norm(diff) / np.asarray(blurry).size)
+        if create:
+            out_dir = Path(foldername + "scale_" + str(i + 1) + "_recon/")
+            out_dir.mkdir(parents=True, exist_ok=True)
+            blurry.save(str(out_dir / png_name))
+    return sizes, rescale_losses, scale_factor, n_scales

@@ -1,0 +1,302 @@
+"""MultiscaleTrainer (reference: SinDDM/trainer.py:35-285) over the sm_100a diffusion module.
+
+Same constructor keywords, attributes (`model`, `ema_model`, `data_list`, `opt`, `scheduler`, `step`,
+`running_loss`), checkpoint format (`step, model, ema, sched, running_loss, running_scale`) and RNG call
+order per step (multinomial -> randint -> randn, quirk Q7).  New here: data-parallel training under torchrun
+(sinddm_b200.dist) and a loss read-back only every `avg_window` steps instead of a host sync per step.
+
+image2image / clip_sampling / clip_roi_sampling / roi_guided_sampling are out of scope (SURVEY.md section 2,
+rows 7-9) and raise NotImplementedError.
+"""
+from __future__ import annotations
+
+import copy
+import datetime
+from functools import partial
+from pathlib import Path
+
+import torch
+from PIL import Image
+from torch.optim import Adam
+from torch.optim.lr_scheduler import MultiStepLR
+from torch.utils import data
+
+from . import dist as spdist
+from .diffusion import EMA
+from .functions import loss_backwards, num_to_groups
+
+
+def _to_model_range(img: Image.Image) -> torch.Tensor:
+    """transforms.ToTensor() followed by t*2-1 (trainer.py:46-50), without the torchvision dependency."""
+    import numpy as np
+    arr = np.asarray(img.convert('RGB'), dtype=np.uint8)
+    ten = torch.from_numpy(arr.copy()).permute(2, 0, 1).to(torch.float32).div(255)
+    return (ten * 2) - 1
+
+
+class Dataset(data.Dataset):
+    """trainer.py:35-63: always yields the first image of the scale folder (and its blurry `_recon` twin)."""
+
+    def __init__(self, folder, image_size, blurry_img=False, exts=['jpg', 'jpeg', 'png']):
+        super().__init__()
+        self.folder = folder
+        self.image_size = image_size
+        self.blurry_img = blurry_img
+        self.paths = [p for ext in exts for p in Path(f'{folder}').glob(f'**/*.{ext}')]
+        if blurry_img:
+            self.folder_recon = folder + '_recon/'
+            self.paths_recon = [p for ext in exts for p in Path(f'{self.folder_recon}').glob(f'**/*.{ext}')]
+        self.transform = _to_model_range
+
+    def __len__(self):
+        return len(self.paths) * 128
+
+    def __getitem__(self, index):
+        img = self.transform(Image.open(self.paths[0]))
+        if self.blurry_img:
+            return img, self.transform(Image.open(self.paths_recon[0]))
+        return img
+
+    def batch(self, batch_size):
+        """What one DataLoader batch of the reference contains: min(batch_size, len(self)) identical rows."""
+        n = min(batch_size, len(self))
+        item = self[0]
+        if self.blurry_img:
+            return tuple(t.unsqueeze(0).repeat(n, 1, 1, 1) for t in item)
+        return item.unsqueeze(0).repeat(n, 1, 1, 1)
+
+
+class MultiscaleTrainer(object):
+
+    def __init__(self, ms_diffusion_model, folder, *, ema_decay=0.995, n_scales=None, scale_factor=1,
+                 image_sizes=None, train_batch_size=32, train_lr=2e-5, train_num_steps=100000,
+                 gradient_accumulate_every=2, fp16=False, step_start_ema=2000, update_ema_every=10,
+                 save_and_sample_every=25000, avg_window=100, sched_milestones=None, results_folder='./results',
+                 device=None):
+        super().__init__()
+        self.device = device
+        self.sched_milestones = [10000, 30000, 60000, 80000, 90000] if sched_milestones is None else sched_milestones
+        image_sizes = [] if image_sizes is None else image_sizes
+        self.model = ms_diffusion_model
+        self.ema = EMA(ema_decay)
+        self.ema_model = copy.deepcopy(self.model)
+        self.update_ema_every = update_ema_every
+        self.step_start_ema = step_start_ema
+        self.save_and_sample_every = save_and_sample_every
+        self.avg_window = avg_window
+
+        self.batch_size = train_batch_size           # GLOBAL batch (split over ranks under torchrun)
+        self.n_scales = n_scales
+        self.scale_factor = scale_factor
+        self.gradient_accumulate_every = gradient_accumulate_every
+        self.train_num_steps = train_num_steps
+
+        # data parallel setup (no-op outside torchrun)
+        self.rank, self.world = spdist.rank(), spdist.world_size()
+        self.local_batch = spdist.shard_batch(train_batch_size, self.world)
+        for m in (self.model, self.ema_model):
+            if hasattr(m, 'set_data_parallel'):
+                m.set_data_parallel(self.rank, self.world)
+
+        self.input_paths = []
+        self.ds_list = []
+        self.data_list = []
+        self.results_folder = Path(results_folder)
+        if self.rank == 0:
+            self.results_folder.mkdir(parents=True, exist_ok=True)
+
+        # one (orig, blurry) batch per scale, resident on the device for the whole run (trainer.py:120-132)
+        for i in range(n_scales):
+            self.input_paths.append(folder + 'scale_' + str(i))
+            ds = Dataset(self.input_paths[i], image_sizes[i] if i < len(image_sizes) else None, blurry_img=i > 0)
+            self.ds_list.append(ds)
+            if i > 0:
+                orig, blur = ds.batch(self.local_batch)
+                self.data_list.append((orig.to(self.device), blur.to(self.device)))
+            else:
+                orig = ds.batch(self.local_batch)
+                self.data_list.append((orig.to(self.device), orig.clone().to(self.device)))
+
+        self.opt = Adam(ms_diffusion_model.parameters(), lr=train_lr)
+        self.scheduler = MultiStepLR(self.opt, milestones=self.sched_milestones, gamma=0.5)
+        self.bucket = spdist.GradientBucket(ms_diffusion_model.parameters())
+
+        self.step = 0
+        self.running_loss = []
+        self.running_scale = []
+        self.avg_t = []
+
+        assert not fp16, 'Apex must be installed in order for mixed precision training to be turned on'
+        self.fp16 = fp16
+        self.reset_parameters()
+
+    # ---------------------------------------------------------------------------------------------
+    def reset_parameters(self):
+        self.ema_model.load_state_dict(self.model.state_dict())
+
+    def step_ema(self):
+        """trainer.py:155-159: hard copy until step_start_ema, EMA afterwards (quirk Q8)."""
+        if self.step < self.step_start_ema:
+            self.reset_parameters()
+            return
+        self.ema.update_model_average(self.ema_model, self.model)
+
+    def save(self, milestone):
+        """trainer.py:161-177 (rank 0 only; the loss plot needs matplotlib and is skipped when it is absent)."""
+        if self.rank != 0:
+            return
+        payload = {
+            'step': self.step,
+            'model': self.model.state_dict(),
+            'ema': self.ema_model.state_dict(),
+            'sched': self.scheduler.state_dict(),
+            'running_loss': self.running_loss,
+            'running_scale': self.running_scale,
+        }
+        torch.save(payload, str(self.results_folder / f'model-{milestone}.pt'))
+        try:
+            from matplotlib import pyplot as plt
+        except Exception:
+            return
+        plt.rcParams['figure.figsize'] = [16, 8]
+        plt.plot(self.running_loss)
+        plt.grid(True)
+        plt.ylim((0, 0.2))
+        plt.savefig(str(self.results_folder / 'running_loss'))
+        plt.clf()
+
+    def load(self, milestone):
+        """trainer.py:179-187 (optimizer state is not part of the checkpoint, quirk Q12)."""
+        ckpt = torch.load(str(self.results_folder / f'model-{milestone}.pt'), map_location=self.device)
+        self.step = ckpt['step']
+        self.model.load_state_dict(ckpt['model'])
+        self.ema_model.load_state_dict(ckpt['ema'])
+        self.scheduler.load_state_dict(ckpt['sched'])
+        self.running_loss = ckpt['running_loss']
+
+    # ---------------------------------------------------------------------------------------------
+    def train_step(self, s=None):
+        """One optimizer step (trainer.py:196-214).  Returns the (device, fp32) loss of the last micro-batch."""
+        if s is None:
+            s = torch.multinomial(input=self._s_weights, num_samples=1)
+        s = int(s)                                        # the reference syncs here too (list index by tensor)
+        loss = None
+        for _ in range(self.gradient_accumulate_every):
+            batch = self.data_list[s]
+            loss = self.model(batch, s)
+            self._loss_acc += loss.detach().double()
+            loss_backwards(self.fp16, loss / self.gradient_accumulate_every, self.opt)
+        self.bucket.all_reduce_mean()
+        if self.step % self.avg_window == 0:
+            acc = self._loss_acc.clone()
+            if self.world > 1:
+                import torch.distributed as tdist
+                tdist.all_reduce(acc)
+                acc /= self.world
+            avg = float(acc.item()) / self.avg_window     # first report divides one loss by the window (Q5)
+            if self.rank == 0:
+                print(f'step:{self.step} loss:{avg}')
+            self.running_loss.append(avg)
+            self._loss_acc.zero_()
+        self.opt.step()
+        self.opt.zero_grad()
+        if self.step % self.update_ema_every == 0:
+            self.step_ema()
+        self.scheduler.step()
+        self.step += 1
+        return loss
+
+    def _prepare_training(self):
+        self._s_weights = torch.tensor(self.model.num_timesteps_trained, device=self.device, dtype=torch.float)
+        if not hasattr(self, '_loss_acc'):
+            self._loss_acc = torch.zeros((), dtype=torch.float64, device=self.device)
+
+    def train(self):
+        self._prepare_training()
+        while self.step < self.train_num_steps:
+            self.train_step()
+            if self.step % self.save_and_sample_every == 0:
+                milestone = self.step // self.save_and_sample_every
+                batches = num_to_groups(16, self.batch_size)
+                images = torch.cat([self.ema_model.sample(batch_size=n) for n in batches], dim=0)
+                images = (images + 1) * 0.5
+                if self.rank == 0:
+                    from torchvision import utils
+                    utils.save_image(images, str(self.results_folder / f'sample-{milestone}.png'), nrow=4)
+                self.save(milestone)
+        if self.rank == 0:
+            print('training completed')
+
+    # ---------------------------------------------------------------------------------------------
+    def sample_scales(self, scale_mul=None, batch_size=16, custom_sample=False, custom_image_size_idxs=None,
+                      custom_scales=None, image_name='', start_noise=True, custom_t_list=None, desc=None,
+                      save_unbatched=True, save_images=True):
+        """trainer.py:226-285: coarse-to-fine sampling driver, always on the EMA model.  Under torchrun each
+        rank generates batch_size / world_size images (no collective).  Returns the list of per-scale
+        batches; `save_images=False` skips the PNG writes (benchmarks)."""
+        ema = self.ema_model
+        if desc is None:
+            desc = f'sample_{str(datetime.datetime.now()).replace(":", "_")}'
+        if ema.reblurring:
+            desc = desc + '_rblr'
+        if ema.sample_limited_t:
+            desc = desc + '_t_lmtd'
+        if custom_t_list is None:
+            custom_t_list = ema.num_timesteps_ideal[1:]
+        if custom_scales is None:
+            custom_scales = [*range(self.n_scales)]
+            n_scales = self.n_scales
+        else:
+            n_scales = len(custom_scales)
+        if custom_image_size_idxs is None:
+            custom_image_size_idxs = [*range(self.n_scales)]
+        local_b = spdist.shard_batch(batch_size, self.world)
+
+        samples = []
+        out_dir = Path(str(self.results_folder / 'final_samples'))
+        if save_images and self.rank == 0:
+            out_dir.mkdir(parents=True, exist_ok=True)
+        if scale_mul is not None:
+            base = self.model.image_sizes[custom_image_size_idxs[0]]
+            scale_0_size = (int(base[0] * scale_mul[0]), int(base[1] * scale_mul[1]))
+        else:
+            scale_0_size = None
+        t_list = [ema.num_timesteps_trained[0]] + custom_t_list
+        prefix = '_'.join(str(e) for e in t_list)
+        final_img = None
+        for i in range(n_scales):
+            if start_noise and i == 0:
+                samples.append(ema.sample(batch_size=local_b, scale_0_size=scale_0_size, s=custom_scales[i]))
+            elif i == 0:       # inject the training image instead of noise
+                first = Image.open(self.input_paths[custom_scales[i]] + '/' + image_name)
+                samples.append(_to_model_range(first).repeat(local_b, 1, 1, 1).to(self.device))
+            else:
+                samples.append(ema.sample_via_scale(local_b, samples[i - 1], s=custom_scales[i],
+                                                    scale_mul=scale_mul, custom_sample=custom_sample,
+                                                    custom_img_size_idx=custom_image_size_idxs[i],
+                                                    custom_t=custom_t_list[int(custom_scales[i]) - 1]))
+            final_img = (samples[i] + 1) * 0.5
+            if save_images and self.rank == 0:
+                from torchvision import utils
+                utils.save_image(final_img, str(out_dir / prefix) +
+                                 f'_out_s{i}_{desc}_sm_{scale_mul[0]}_{scale_mul[1]}.png', nrow=4)
+        if save_images and save_unbatched and self.rank == 0:
+            from torchvision import utils
+            out_dir = Path(str(self.results_folder / f'final_samples_unbatched_{desc}'))
+            out_dir.mkdir(parents=True, exist_ok=True)
+            for b in range(final_img.shape[0]):
+                utils.save_image(final_img[b], str(out_dir / prefix) + f'_out_b{b}.png')
+        return samples
+
+    # ---------------------------------------------------------------------------------------------
+    def image2image(self, *args, **kwargs):
+        raise NotImplementedError('harmonization / style transfer is outside the sinddm_b200 hot path')
+
+    def clip_sampling(self, *args, **kwargs):
+        raise NotImplementedError('CLIP-guided sampling is outside the sinddm_b200 hot path')
+
+    def clip_roi_sampling(self, *args, **kwargs):
+        raise NotImplementedError('CLIP-guided sampling is outside the sinddm_b200 hot path')
+
+    def roi_guided_sampling(self, *args, **kwargs):
+        raise NotImplementedError('ROI-guided sampling is outside the sinddm_b200 hot path')
