@@ -1,0 +1,70 @@
+"""The C-ABI library loads on a CPU-only box and exports exactly what include/sinddm_b200.h declares.
+No compute is launched here."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+import torch
+
+REPO = Path(__file__).resolve().parents[1]
+HEADER = REPO / "include" / "sinddm_b200.h"
+
+
+def declared_functions():
+    text = HEADER.read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = re.findall(r"^\s*(?:int|size_t|void|const char\*)\s+(sinddm_\w+)\s*\(", text, flags=re.M)
+    return sorted(set(names))
+
+
+def test_header_declares_the_expected_surface():
+    names = declared_functions()
+    assert len(names) >= 24
+    for must in ("sinddm_init", "sinddm_net_forward", "sinddm_net_backward", "sinddm_conv_forward",
+                 "sinddm_conv_wgrad", "sinddm_dw5x5", "sinddm_ddpm_step", "sinddm_qsample_mix", "sinddm_l1_loss"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol():
+    from sinddm_b200 import _capi
+    lib = _capi.load()                      # raises if the .so is missing: there is no fallback
+    for name in declared_functions():
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+        assert name in _capi.SIGNATURES, f"{name} has no ctypes signature"
+    assert sorted(_capi.SIGNATURES) == declared_functions()
+    assert lib.sinddm_abi_version() == 1
+
+
+def test_workspace_queries_run_without_a_gpu():
+    from sinddm_b200 import _capi
+    lib = _capi.load()
+    infer = lib.sinddm_plan_workspace_bytes(16, 186, 248, 160, 3, _capi.MATH_TF32, 0)
+    train = lib.sinddm_plan_workspace_bytes(32, 186, 248, 160, 3, _capi.MATH_TF32, 1)
+    assert 0 < infer < train < 40 * 2**30
+    assert lib.sinddm_plan_workspace_bytes(0, 1, 1, 160, 3, 1, 0) == 0
+    assert lib.sinddm_l1_loss_workspace_bytes() > 0
+    assert lib.sinddm_conv_wgrad_workspace_bytes(2, 19, 23, 80, 80, 9, 1) > 0
+
+
+def test_product_path_refuses_cpu_tensors():
+    """No CPU fallback: CPU tensors (or a missing device) are an error, never a silent slow path."""
+    from sinddm_b200 import SinDDMNet, ops, _capi
+    net = SinDDMNet(dim=16, multiscale=True)
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 3, 8, 8), torch.zeros(1, dtype=torch.long), 0)
+    with pytest.raises(RuntimeError):
+        ops.colsum(torch.zeros(4, 4))
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            _capi.init(0)
+
+
+def test_product_never_imports_the_oracle():
+    for py in (REPO / "sinddm_b200").rglob("*.py"):
+        src = py.read_text()
+        assert "import oracle" not in src and "from oracle" not in src, py
+    for py in list((REPO / "SinDDM").glob("*.py")) + [REPO / "main.py"]:
+        if py.exists():
+            src = py.read_text()
+            assert "oracle" not in src, py

@@ -1,0 +1,115 @@
+"""Host-side logic that needs no GPU: module surface / state_dict contract, EMA, trainer bookkeeping pieces."""
+import copy
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_SCALE_LOSSES, GOLDEN_SIZES
+from oracle import sinddm_oracle as orc
+
+
+def make(dim=160):
+    from sinddm_b200 import MultiScaleGaussianDiffusion, SinDDMNet
+    net = SinDDMNet(dim=dim, multiscale=True)
+    dif = MultiScaleGaussianDiffusion(denoise_fn=net, n_scales=5, scale_factor=1.36, image_sizes=GOLDEN_SIZES,
+                                      timesteps=100, train_full_t=True, scale_losses=GOLDEN_SCALE_LOSSES,
+                                      results_folder=tempfile.mkdtemp())
+    return net, dif
+
+
+def test_state_dict_contract_65_keys():
+    """13 buffers + 52 denoise_fn.* parameters, names and shapes of the reference."""
+    net, dif = make()
+    sd = dif.state_dict()
+    assert len(sd) == 65
+    expect = [("denoise_fn." + n, s) for n, s in orc.param_shapes(160)]
+    got = [(k, tuple(v.shape)) for k, v in sd.items() if k.startswith("denoise_fn.")]
+    assert got == expect
+    assert [n for n, _ in net.named_parameters()] == [n for n, _ in orc.param_shapes(160)]
+    assert sum(p.numel() for p in net.parameters()) == 1_106_772
+
+
+def test_drop_in_import_paths():
+    import SinDDM.functions as F
+    import SinDDM.models as M
+    import SinDDM.trainer as T
+    from text2live_util.util import get_augmentations_template  # noqa: F401
+    from text2live_util.clip_extractor import ClipExtractor  # noqa: F401
+    for name in ("SinDDMNet", "MultiScaleGaussianDiffusion", "EMA", "SinDDMConvBlock", "SinusoidalPosEmb"):
+        assert hasattr(M, name)
+    assert hasattr(T, "MultiscaleTrainer") and hasattr(T, "Dataset")
+    for name in ("create_img_scales", "extract", "cosine_beta_schedule", "noise_like", "default", "exists",
+                 "num_to_groups", "cycle", "loss_backwards"):
+        assert hasattr(F, name)
+
+
+def test_helpers_match_reference_semantics():
+    from sinddm_b200.functions import cosine_beta_schedule, default, extract, num_to_groups
+    assert num_to_groups(16, 32) == [16]
+    assert num_to_groups(70, 32) == [32, 32, 6]
+    assert default(None, lambda: 5) == 5 and default(3, 4) == 3
+    a = torch.arange(10.0)
+    t = torch.tensor([1, 7])
+    assert extract(a, t, (2, 3, 4, 4)).shape == (2, 1, 1, 1)
+    np.testing.assert_array_equal(cosine_beta_schedule(100), orc.cosine_beta_schedule(100))
+
+
+def test_sinusoidal_embedding_matches_oracle():
+    from sinddm_b200 import SinusoidalPosEmb
+    x = torch.tensor([0, 3, 99])
+    assert torch.equal(SinusoidalPosEmb(32)(x), orc.sinusoidal_pos_emb(x, 32))
+
+
+def test_deepcopy_and_ema_semantics():
+    from sinddm_b200 import EMA
+    net, dif = make(dim=16)
+    twin = copy.deepcopy(dif)                        # trainer.py:100
+    assert twin.denoise_fn._runtime is not dif.denoise_fn._runtime
+    with torch.no_grad():
+        for p in dif.parameters():
+            p.add_(1.0)
+    before = [p.clone() for p in twin.parameters()]
+    EMA(0.995).update_model_average(twin, dif)
+    for b, new, cur in zip(before, twin.parameters(), dif.parameters()):
+        assert torch.allclose(new, b * 0.995 + (1 - 0.995) * cur)
+
+
+def test_checkpoint_keys_load_like_the_authors_files():
+    """A state_dict with the reference's 65 keys loads strictly (the shipped model-12.pt files have them)."""
+    net, dif = make()
+    sd = {("denoise_fn." + k): v for k, v in orc.synthetic_params(5, 160).items()}
+    sd.update(orc.Schedule(5, GOLDEN_SCALE_LOSSES, 100, train_full_t=True).buffers())
+    missing = dif.load_state_dict(sd, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+
+
+def test_guidance_modes_refuse_loudly():
+    from sinddm_b200 import MultiscaleTrainer
+    net, dif = make(dim=16)
+    dif.clip_guided_sampling = True
+    with pytest.raises(NotImplementedError):
+        dif._refuse_guidance()
+    for name in ("image2image", "clip_sampling", "clip_roi_sampling", "roi_guided_sampling"):
+        with pytest.raises(NotImplementedError):
+            getattr(MultiscaleTrainer, name)(None)
+
+
+def test_dataset_yields_first_image_replicated(tmp_path):
+    from PIL import Image
+    from sinddm_b200.trainer import Dataset
+    d0 = tmp_path / "scale_1"
+    d1 = tmp_path / "scale_1_recon"
+    d0.mkdir(); d1.mkdir()
+    rs = np.random.RandomState(0)
+    a = rs.randint(0, 255, (9, 11, 3), dtype=np.uint8)
+    b = rs.randint(0, 255, (9, 11, 3), dtype=np.uint8)
+    Image.fromarray(a).save(d0 / "img.png")
+    Image.fromarray(b).save(d1 / "img.png")
+    ds = Dataset(str(d0), None, blurry_img=True)
+    assert len(ds) == 128
+    orig, blur = ds.batch(200)                       # the reference's DataLoader caps at len(ds) = 128
+    assert orig.shape == (128, 3, 9, 11) and blur.shape == (128, 3, 9, 11)
+    assert torch.equal(orig[0], torch.from_numpy(a).permute(2, 0, 1).float() / 255 * 2 - 1)
+    assert torch.equal(blur[5], torch.from_numpy(b).permute(2, 0, 1).float() / 255 * 2 - 1)
