@@ -52,6 +52,14 @@ int sinddm_init(int device);
 const char* sinddm_last_error(void);
 int sinddm_abi_version(void);
 
+/* Number of kernels this library has launched so far in the process (bench.py's gpu_launches). */
+unsigned long long sinddm_launch_count(void);
+/* Per-kernel CUDA-event timing on the launching stream, off by default.  kind 0 = tcgen05 conv (forward /
+ * data gradient), 1 = tcgen05 weight gradient.  collect() synchronises on the recorded events and returns the
+ * summed duration, algorithmic FLOPs (2 x real pixels x N x K) and launch count since enable(1). */
+void sinddm_profile_enable(int on);
+int sinddm_profile_collect(int kind, double* total_ms, double* total_flops, int* launches);
+
 /* ---- whole denoiser: SinDDMNet.forward and its autograd backward (SinDDM/models.py:134-151) ---- */
 
 typedef struct sinddm_plan sinddm_plan;

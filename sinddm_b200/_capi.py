@@ -57,6 +57,9 @@ SIGNATURES = {
     "sinddm_init": (_i, [_i]),
     "sinddm_last_error": (C.c_char_p, []),
     "sinddm_abi_version": (_i, []),
+    "sinddm_launch_count": (C.c_ulonglong, []),
+    "sinddm_profile_enable": (None, [_i]),
+    "sinddm_profile_collect": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i)]),
     "sinddm_plan_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
     "sinddm_plan_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i, _i, _i, _vp, _sz]),
     "sinddm_plan_destroy": (None, [_vp]),

@@ -21,6 +21,12 @@ extern "C" {
 int sinddm_init(int device) { return init_device(device); }
 const char* sinddm_last_error(void) { return last_error(); }
 int sinddm_abi_version(void) { return SINDDM_ABI_VERSION; }
+unsigned long long sinddm_launch_count(void) { return launch_count(); }
+void sinddm_profile_enable(int on) { prof_enable(on); }
+int sinddm_profile_collect(int kind, double* total_ms, double* total_flops, int* launches) {
+    SINDDM_REQUIRE(total_ms && total_flops && launches, "profile_collect: NULL argument");
+    return prof_collect(kind, total_ms, total_flops, launches);
+}
 
 size_t sinddm_plan_workspace_bytes(int B, int H, int W, int dim, int channels, int math, int training) {
     if (B < 1 || H < 1 || W < 1 || dim < 2 || channels < 1) return 0;

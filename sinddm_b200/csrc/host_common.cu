@@ -19,6 +19,68 @@ void set_error(const char* fmt, ...) {
 
 const char* last_error() { return g_err; }
 
+static unsigned long long g_launches = 0;
+
+void note_call(const char* expr) {
+    // "cudaGetLastError()" is what follows every <<<>>> launch in this library
+    if (expr[0] == 'c' && expr[4] == 'G' && expr[7] == 'L') ++g_launches;
+}
+
+unsigned long long launch_count() { return g_launches; }
+
+namespace {
+struct ProfEntry {
+    cudaEvent_t a, b;
+    double flops;
+    int kind;
+};
+constexpr int kProfMax = 8192;
+ProfEntry g_prof[kProfMax];
+int g_prof_n = 0, g_prof_made = 0, g_prof_on = 0, g_prof_open = -1;
+}  // namespace
+
+void prof_enable(int on) {
+    g_prof_on = on;
+    if (on) g_prof_n = 0;
+}
+
+void prof_begin(cudaStream_t stream, int kind, double flops) {
+    g_prof_open = -1;
+    if (!g_prof_on || g_prof_n >= kProfMax) return;
+    if (g_prof_n >= g_prof_made) {
+        if (cudaEventCreate(&g_prof[g_prof_made].a) != cudaSuccess) return;
+        if (cudaEventCreate(&g_prof[g_prof_made].b) != cudaSuccess) return;
+        ++g_prof_made;
+    }
+    g_prof_open = g_prof_n++;
+    g_prof[g_prof_open].flops = flops;
+    g_prof[g_prof_open].kind = kind;
+    cudaEventRecord(g_prof[g_prof_open].a, stream);
+}
+
+void prof_end(cudaStream_t stream) {
+    if (g_prof_open >= 0) cudaEventRecord(g_prof[g_prof_open].b, stream);
+    g_prof_open = -1;
+}
+
+int prof_collect(int kind, double* total_ms, double* total_flops, int* launches) {
+    double ms = 0, fl = 0;
+    int n = 0;
+    for (int i = 0; i < g_prof_n; ++i) {
+        if (g_prof[i].kind != kind) continue;
+        SINDDM_CUDA_OK(cudaEventSynchronize(g_prof[i].b));
+        float t = 0.f;
+        SINDDM_CUDA_OK(cudaEventElapsedTime(&t, g_prof[i].a, g_prof[i].b));
+        ms += t;
+        fl += g_prof[i].flops;
+        ++n;
+    }
+    *total_ms = ms;
+    *total_flops = fl;
+    *launches = n;
+    return SINDDM_OK;
+}
+
 static DeviceInfo g_dev = {0, -1, 0, 0};
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 

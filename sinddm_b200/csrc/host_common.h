@@ -23,6 +23,7 @@ const char* last_error();
 #define SINDDM_CUDA_OK(expr)                                                                   \
     do {                                                                                       \
         cudaError_t _e = (expr);                                                               \
+        ::sinddm::note_call(#expr);                                                            \
         if (_e != cudaSuccess) {                                                               \
             ::sinddm::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
             return ::sinddm::SINDDM_ERR_CUDA;                                                  \
@@ -61,6 +62,18 @@ int make_tmap_nhwc(CUtensorMap* out, const float* base, int B, int H, int W, int
 // [rows, inner] fp32 row-major matrix -> 2-D tiled TMA descriptor, box = (box_inner, box_rows).
 int make_tmap_2d(CUtensorMap* out, const float* base, int inner, int rows, int box_inner, int box_rows,
                  CUtensorMapSwizzle swizzle);
+
+// Every kernel launch is followed by SINDDM_CUDA_OK(cudaGetLastError()); note_call counts those, which
+// gives bench.py its `gpu_launches` figure (sinddm_launch_count in the C ABI).
+void note_call(const char* expr);
+unsigned long long launch_count();
+
+// Optional per-kernel timing with CUDA events on the launching stream (bench.py's live roofline numbers).
+// kind: 0 = tc_conv (forward / data gradient), 1 = tc_wgrad.  Off by default; zero cost when off.
+void prof_enable(int on);
+void prof_begin(cudaStream_t stream, int kind, double flops);
+void prof_end(cudaStream_t stream);
+int prof_collect(int kind, double* total_ms, double* total_flops, int* launches);
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

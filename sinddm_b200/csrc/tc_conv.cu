@@ -371,7 +371,10 @@ int tc_conv_launch(const TcConvOp& op, cudaStream_t stream) {
     a.stage_bytes = op.stage_bytes;
     a.idesc = umma_idesc_tf32(kBM, p.N, 0, 0);
     a.ep = p.ep;
+    // algorithmic work: real pixels x N x (taps*Cin + Cres) MACs
+    prof_begin(stream, 0, 2.0 * (double)p.B * p.H * p.W * p.N * ((double)p.ntaps * p.Cin + a.Cres));
     tc_conv_kernel<<<op.grid, kThreads, op.smem_bytes, stream>>>(op.tm_a, op.tm_ares, op.tm_b, op.tm_bres, a);
+    prof_end(stream);
     SINDDM_CUDA_OK(cudaGetLastError());
     return SINDDM_OK;
 }

@@ -27,7 +27,6 @@ constexpr int kKP = 32;                   // pixels per K step
 constexpr int kCC = 32;                   // channels per chunk box
 constexpr int kBoxBytes = kKP * kCC * 4;  // 4 KiB
 constexpr int kThreads = 192;
-constexpr int kMaxSlots = 16;             // 4 M-tiles x 4 chunks
 
 struct KernelArgs {
     int B, H, W;
@@ -287,7 +286,9 @@ int tc_wgrad_launch(const TcWgradOp& op, cudaStream_t stream) {
     a.idesc = umma_idesc_tf32(128, p.Cy, 1, 1);
     a.partial = p.partial;
     dim3 grid(p.nsplit, op.ngroups);
+    prof_begin(stream, 1, 2.0 * (double)p.B * p.H * p.W * p.ntaps * p.Cx * p.Cy);
     tc_wgrad_kernel<<<grid, kThreads, op.smem_bytes, stream>>>(op.tm_x, op.tm_dy, a);
+    prof_end(stream);
     SINDDM_CUDA_OK(cudaGetLastError());
     return SINDDM_OK;
 }

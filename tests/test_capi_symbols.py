@@ -14,7 +14,7 @@ HEADER = REPO / "include" / "sinddm_b200.h"
 def declared_functions():
     text = HEADER.read_text()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    names = re.findall(r"^\s*(?:int|size_t|void|const char\*)\s+(sinddm_\w+)\s*\(", text, flags=re.M)
+    names = re.findall(r"^\s*(?:int|size_t|void|const char\*|unsigned long long)\s+(sinddm_\w+)\s*\(", text, flags=re.M)
     return sorted(set(names))
 
 
