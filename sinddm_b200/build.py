@@ -25,6 +25,7 @@ SOURCES = [
     "tc_wgrad.cu",
     "simt_conv.cu",
     "simt_misc.cu",
+    "dw_kernels.cu",
     "cond.cu",
     "diffusion_ops.cu",
     "net.cu",

@@ -1,0 +1,220 @@
+// Depthwise 5x5 (+bias +conditioning) and its gradients on NHWC fp32 -- HBM-bound kernels.
+//
+// dw5x5 replaces `h = self.ds_conv(x); h = h + condition` (reference SinDDM/models.py:61,70,77); with
+// flip=1 it is the data gradient; dw5x5_wgrad replaces what autograd derives for ds_conv.weight / bias and
+// for the conditioning vector.
+//
+// Layout of the work: one thread owns ONE channel of one row segment (b, h, 64 px) and slides a 5x5 register
+// window along W.  Adjacent threads are adjacent channels, so every global access of a warp is one
+// contiguous 128-byte line; per output pixel a thread loads 5 new inputs (the window's new column) instead
+// of 25, and the 25 weights live in registers.
+#include "common.cuh"
+#include "ops.h"
+
+namespace sinddm {
+
+namespace {
+
+constexpr int kSeg = 64;  // pixels per row segment
+
+struct RowWindow {
+    // win[ky][slot]: slot = image column modulo 5
+    float v[5][5];
+};
+
+// loads column `col` of the 5 input rows around h into slot (col mod 5); zero outside the image
+SINDDM_DEVINL void load_column(RowWindow& win, const float* const (&rowp)[5], const bool (&rowok)[5], int col, int W,
+                               int C, int slot) {
+    const bool ok = col >= 0 && col < W;
+#pragma unroll
+    for (int ky = 0; ky < 5; ++ky) win.v[ky][slot] = (ok && rowok[ky]) ? __ldg(rowp[ky] + (size_t)col * C) : 0.f;
+}
+
+template <typename Body>
+SINDDM_DEVINL void slide_row(const float* __restrict__ in, int b, int h, int w0, int w1, int c, int H, int W, int C,
+                             Body&& body) {
+    const float* rowp[5];
+    bool rowok[5];
+#pragma unroll
+    for (int ky = 0; ky < 5; ++ky) {
+        const int hh = h + ky - 2;
+        rowok[ky] = hh >= 0 && hh < H;
+        rowp[ky] = in + (((size_t)b * H + (rowok[ky] ? hh : 0)) * W) * C + c;
+    }
+    RowWindow win;
+    // columns w0-2 .. w0+1 are needed before the first output; slots are (column + 10) % 5
+    const int base = w0 - 2;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) load_column(win, rowp, rowok, base + j, W, C, j);
+    // process 5 outputs per outer iteration so window slots are compile-time constants
+    for (int w = w0; w < w1; w += 5) {
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const int wo = w + j;
+            if (wo < w1) {
+                // new column wo+2 -> slot (4 + j) % 5 ; taps kx=0..4 read slots (j + kx) % 5
+                load_column(win, rowp, rowok, wo + 2, W, C, (4 + j) % 5);
+                float x[5][5];
+#pragma unroll
+                for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 5; ++kx) x[ky][kx] = win.v[ky][(j + kx) % 5];
+                body(wo, x);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+dw5x5_kernel(const float* __restrict__ in, const float* __restrict__ wgt, const float* __restrict__ bias,
+             const float* __restrict__ cond, const float* __restrict__ add, float* __restrict__ out, int B, int H,
+             int W, int C, int flip, int round) {
+    const int nseg = (W + kSeg - 1) / kSeg;
+    const long long total = (long long)B * H * nseg * C;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c = (int)(idx % C);
+    long long r = idx / C;
+    const int seg = (int)(r % nseg);
+    r /= nseg;
+    const int h = (int)(r % H);
+    const int b = (int)(r / H);
+
+    float wr[5][5];
+#pragma unroll
+    for (int t = 0; t < 25; ++t) wr[t / 5][t % 5] = __ldg(wgt + c * 25 + (flip ? 24 - t : t));
+    const float bv = bias ? __ldg(bias + c) : 0.f;
+    const float cv = cond ? __ldg(cond + (size_t)b * C + c) : 0.f;
+    const int w0 = seg * kSeg;
+    const int w1 = min(W, w0 + kSeg);
+    const size_t rowoff = (((size_t)b * H + h) * W) * C + c;
+
+    slide_row(in, b, h, w0, w1, c, H, W, C, [&](int wo, const float (&x)[5][5]) {
+        float acc = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 5; ++kx) acc = fmaf(x[ky][kx], wr[ky][kx], acc);
+        const size_t off = rowoff + (size_t)wo * C;
+        float v = (acc + bv) + cv;               // reference order: (conv + bias) + condition
+        if (add) v += __ldg(add + off);
+        if (round) v = round_tf32(v);
+        out[off] = v;
+    });
+}
+
+// ---------------------------------------------------------------------------------------------------
+// gradients of the depthwise weight / bias / conditioning vector
+//   grid = B * nchunk CTAs (chunk = kRowsPerChunk image rows), block = (C, lanes)
+//   thread (c, lane) walks the chunk's (row, segment) units lane, lane+lanes, ... with the sliding window,
+//   accumulates 25 tap sums + 1 plain sum, smem-reduces over lanes -> scratch[b][chunk][26][C]
+// ---------------------------------------------------------------------------------------------------
+constexpr int kRowsPerChunk = 8;
+
+__global__ void __launch_bounds__(512)
+dw5x5_wgrad_partial_kernel(const float* __restrict__ x, const float* __restrict__ dh,
+                                           float* __restrict__ scratch, int B, int H, int W, int C, int nchunk) {
+    extern __shared__ float red[];  // [lanes][26][C]
+    const int c = threadIdx.x;
+    const int ly = threadIdx.y;
+    const int lanes = blockDim.y;
+    const int chunk = blockIdx.x % nchunk;
+    const int b = blockIdx.x / nchunk;
+    const int h_begin = chunk * kRowsPerChunk;
+    const int h_end = min(H, h_begin + kRowsPerChunk);
+    const int nseg = (W + kSeg - 1) / kSeg;
+    const int nunits = (h_end - h_begin) * nseg;
+
+    float acc[5][5];
+#pragma unroll
+    for (int t = 0; t < 25; ++t) acc[t / 5][t % 5] = 0.f;
+    float gsum = 0.f;
+
+    for (int u = ly; u < nunits; u += lanes) {
+        const int h = h_begin + u / nseg;
+        const int w0 = (u % nseg) * kSeg;
+        const int w1 = min(W, w0 + kSeg);
+        const float* dhrow = dh + (((size_t)b * H + h) * W) * C + c;
+        slide_row(x, b, h, w0, w1, c, H, W, C, [&](int wo, const float (&xv)[5][5]) {
+            const float g = __ldg(dhrow + (size_t)wo * C);
+            gsum += g;
+#pragma unroll
+            for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 5; ++kx) acc[ky][kx] = fmaf(xv[ky][kx], g, acc[ky][kx]);
+        });
+    }
+#pragma unroll
+    for (int t = 0; t < 25; ++t) red[(ly * 26 + t) * C + c] = acc[t / 5][t % 5];
+    red[(ly * 26 + 25) * C + c] = gsum;
+    __syncthreads();
+    if (ly == 0) {
+        for (int i = 0; i < 26; ++i) {
+            float s = 0.f;
+            for (int y = 0; y < lanes; ++y) s += red[(y * 26 + i) * C + c];
+            scratch[(((size_t)b * nchunk + chunk) * 26 + i) * C + c] = s;
+        }
+    }
+}
+
+// stage 2: dcond[b][c] = sum_chunk s[b][chunk][25][c]; dw[c][tap] = sum_b sum_chunk s[..][tap][c]; db = sum_b dcond
+__global__ void dw5x5_wgrad_final_kernel(const float* __restrict__ scratch, float* __restrict__ dw,
+                                         float* __restrict__ db, float* __restrict__ dcond, int B, int C, int nchunk) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const int i = blockIdx.y;  // 0..25
+    float tot = 0.f;
+    for (int b = 0; b < B; ++b) {
+        float s = 0.f;
+        for (int k = 0; k < nchunk; ++k) s += scratch[(((size_t)b * nchunk + k) * 26 + i) * C + c];
+        if (i == 25 && dcond) dcond[(size_t)b * C + c] = s;
+        tot += s;
+    }
+    if (i == 25) {
+        if (db) db[c] = tot;
+    } else if (dw) {
+        dw[c * 25 + i] = tot;
+    }
+}
+
+}  // namespace
+
+int dw5x5_launch(const float* in, const float* w, const float* bias, const float* cond, const float* add, float* out,
+                 int B, int H, int W, int C, int flip, int round_tf32, cudaStream_t stream) {
+    const int nseg = ceil_div(W, kSeg);
+    const long long total = (long long)B * H * nseg * C;
+    const long long blocks = (total + 255) / 256;
+    SINDDM_REQUIRE(blocks < (1ll << 31), "dw5x5: problem too large");
+    dw5x5_kernel<<<(unsigned)blocks, 256, 0, stream>>>(in, w, bias, cond, add, out, B, H, W, C, flip, round_tf32);
+    SINDDM_CUDA_OK(cudaGetLastError());
+    return SINDDM_OK;
+}
+
+size_t dw5x5_wgrad_scratch_floats(int B, int H, int C) {
+    return (size_t)B * ceil_div(H, kRowsPerChunk) * 26 * C;
+}
+
+int dw5x5_wgrad_launch(const float* x, const float* dh, float* dw, float* db, float* dcond, float* scratch, int B,
+                       int H, int W, int C, cudaStream_t stream) {
+    SINDDM_REQUIRE(C <= 256, "dw5x5_wgrad: C=%d too large", C);
+    const int nchunk = ceil_div(H, kRowsPerChunk);
+    int lanes = 512 / C;
+    if (lanes < 1) lanes = 1;
+    if (lanes > 16) lanes = 16;
+    dim3 block(C, lanes);
+    const size_t smem = (size_t)lanes * 26 * C * sizeof(float);
+    static int attr_set = 0;
+    if (smem > 48 * 1024 && !attr_set) {
+        SINDDM_CUDA_OK(cudaFuncSetAttribute(dw5x5_wgrad_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            96 * 1024));
+        attr_set = 1;
+    }
+    dw5x5_wgrad_partial_kernel<<<B * nchunk, block, smem, stream>>>(x, dh, scratch, B, H, W, C, nchunk);
+    SINDDM_CUDA_OK(cudaGetLastError());
+    dim3 grid2(ceil_div(C, 64), 26);
+    dw5x5_wgrad_final_kernel<<<grid2, 64, 0, stream>>>(scratch, dw, db, dcond, B, C, nchunk);
+    SINDDM_CUDA_OK(cudaGetLastError());
+    return SINDDM_OK;
+}
+
+}  // namespace sinddm

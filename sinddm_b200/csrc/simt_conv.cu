@@ -212,11 +212,212 @@ __global__ void pack_conv_weights_kernel(const float* __restrict__ w, int Cout, 
     if (dst_dgrad) dst_dgrad[((size_t)(ntaps - 1 - tap) * Cin + ci) * Cout + co] = v;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Specialisations for the 3-channel layers (they are HBM / LSU bound, not contractions):
+//   small Cin  (l1.net[0] 3->80 3x3, final_conv data gradient 3->80 1x1): the whole K = ntaps*Cin <= 27
+//              input patch of a pixel sits in registers, weights [K][N] in smem are read as float4 broadcasts;
+//   small N    (data gradient into l1's depthwise output, 80->3 3x3): 3 accumulators per pixel, inputs read as
+//              float4 along the channel dimension, weights [tap][ci][4] in smem.
+// ---------------------------------------------------------------------------------------------------
+SINDDM_DEVINL void conv_epilogue_one(const ConvEpilogue& ep, float v, int n, int N, size_t pix, const float (&x3v)[3],
+                                     float (&fin)[3]) {
+    if (ep.bias) v += ep.bias[n];
+    if (ep.w_res3) {
+        const float* wr = ep.w_res3 + n * 3;
+        v = fmaf(x3v[2], wr[2], fmaf(x3v[1], wr[1], fmaf(x3v[0], wr[0], v)));
+    }
+    const size_t off = pix * N + n;
+    if (ep.res_add) v += ep.res_add[off];
+    if (ep.out_pre) ep.out_pre[off] = v;
+    if (ep.gelu) v = gelu_erf(v);
+    if (ep.dgelu_z) v *= gelu_erf_grad(ep.dgelu_z[off]);
+    if (ep.w_final) {
+        fin[0] = fmaf(v, ep.w_final[0 * N + n], fin[0]);
+        fin[1] = fmaf(v, ep.w_final[1 * N + n], fin[1]);
+        fin[2] = fmaf(v, ep.w_final[2 * N + n], fin[2]);
+    }
+    if (ep.out) ep.out[off] = ep.round_tf32 ? round_tf32(v) : v;
+}
+
+template <int NTAPS, int CIN>
+__global__ void __launch_bounds__(128)
+simt_conv_smallcin_kernel(const ConvProblem p) {
+    constexpr int K = NTAPS * CIN;
+    extern __shared__ __align__(16) float ws[];  // [K][Npad]
+    const int N = p.N;
+    const int Npad = (N + 3) & ~3;
+    for (int i = threadIdx.x; i < K * Npad; i += blockDim.x) {
+        const int n = i % Npad, k = i / Npad;
+        const int tap = k / CIN, ci = k % CIN;
+        ws[i] = n < N ? p.w[((size_t)tap * N + n) * CIN + ci] : 0.f;
+    }
+    __syncthreads();
+    const long long P = (long long)p.B * p.H * p.W;
+    const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= P) return;
+    const int w = (int)(pix % p.W);
+    const int h = (int)((pix / p.W) % p.H);
+    float xin[K];
+#pragma unroll
+    for (int tap = 0; tap < NTAPS; ++tap) {
+        int hh = h, ww = w;
+        if (NTAPS == 9) {
+            hh += tap / 3 - 1;
+            ww += tap % 3 - 1;
+        }
+        const bool ok = hh >= 0 && hh < p.H && ww >= 0 && ww < p.W;
+        const float* src = p.in + (pix + (long long)(hh - h) * p.W + (ww - w)) * CIN;
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) xin[tap * CIN + ci] = ok ? __ldg(src + ci) : 0.f;
+    }
+    float x3v[3] = {0.f, 0.f, 0.f};
+    if (p.ep.x3) {
+        x3v[0] = p.ep.x3[pix * 3 + 0];
+        x3v[1] = p.ep.x3[pix * 3 + 1];
+        x3v[2] = p.ep.x3[pix * 3 + 2];
+    }
+    float fin[3] = {0.f, 0.f, 0.f};
+    for (int n0 = 0; n0 < N; n0 += 4) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const float4 wv = *reinterpret_cast<const float4*>(&ws[k * Npad + n0]);
+            acc.x = fmaf(xin[k], wv.x, acc.x);
+            acc.y = fmaf(xin[k], wv.y, acc.y);
+            acc.z = fmaf(xin[k], wv.z, acc.z);
+            acc.w = fmaf(xin[k], wv.w, acc.w);
+        }
+        const float v[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (n0 + j < N) conv_epilogue_one(p.ep, v[j], n0 + j, N, (size_t)pix, x3v, fin);
+    }
+    if (p.ep.w_final) {
+        const size_t plane = (size_t)p.H * p.W;
+        const int b = (int)(pix / (long long)plane);
+        float* o = p.ep.out_final + (size_t)b * 3 * plane + (size_t)h * p.W + w;
+        o[0] = fin[0] + (p.ep.b_final ? p.ep.b_final[0] : 0.f);
+        o[plane] = fin[1] + (p.ep.b_final ? p.ep.b_final[1] : 0.f);
+        o[2 * plane] = fin[2] + (p.ep.b_final ? p.ep.b_final[2] : 0.f);
+    }
+}
+
+// N <= 4, Cin % 4 == 0
+__global__ void __launch_bounds__(128)
+simt_conv_smalln_kernel(const ConvProblem p) {
+    extern __shared__ __align__(16) float ws[];  // [ntaps][Cin][4]
+    const int N = p.N, C = p.Cin;
+    for (int i = threadIdx.x; i < p.ntaps * C * 4; i += blockDim.x) {
+        const int n = i & 3, ci = (i >> 2) % C, tap = (i >> 2) / C;
+        ws[i] = n < N ? p.w[((size_t)tap * N + n) * C + ci] : 0.f;
+    }
+    __syncthreads();
+    const long long P = (long long)p.B * p.H * p.W;
+    const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= P) return;
+    const int w = (int)(pix % p.W);
+    const int h = (int)((pix / p.W) % p.H);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int tap = 0; tap < p.ntaps; ++tap) {
+        int hh = h, ww = w;
+        if (p.ntaps == 9) {
+            hh += tap / 3 - 1;
+            ww += tap % 3 - 1;
+        }
+        if (hh < 0 || hh >= p.H || ww < 0 || ww >= p.W) continue;
+        const float4* src = reinterpret_cast<const float4*>(p.in + (pix + (long long)(hh - h) * p.W + (ww - w)) * C);
+        const float4* wt = reinterpret_cast<const float4*>(ws + (size_t)tap * C * 4);
+#pragma unroll 4
+        for (int c4 = 0; c4 < C / 4; ++c4) {
+            const float4 xv = __ldg(src + c4);
+            const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 wv = wt[c4 * 4 + j];
+                acc[0] = fmaf(xs[j], wv.x, acc[0]);
+                acc[1] = fmaf(xs[j], wv.y, acc[1]);
+                acc[2] = fmaf(xs[j], wv.z, acc[2]);
+                acc[3] = fmaf(xs[j], wv.w, acc[3]);
+            }
+        }
+    }
+    float x3v[3] = {0.f, 0.f, 0.f};
+    float fin[3] = {0.f, 0.f, 0.f};
+    for (int n = 0; n < N; ++n) conv_epilogue_one(p.ep, acc[n], n, N, (size_t)pix, x3v, fin);
+}
+
+// weight gradient with K = ntaps*Cx <= 32 accumulators per thread: dy is read ONCE for all taps.
+// grid = nsplit, block = (Cy padded to 32, kPY)
+template <int NTAPS, int CX>
+__global__ void simt_wgrad_smallcx_kernel(const WgradProblem p) {
+    constexpr int K = NTAPS * CX;
+    extern __shared__ float red[];  // [kPY][K][blockDim.x]
+    const int split = blockIdx.x;
+    const int co = threadIdx.x, py = threadIdx.y;
+    const long long P = (long long)p.B * p.H * p.W;
+    const long long p_begin = P * split / p.nsplit;
+    const long long p_end = P * (split + 1) / p.nsplit;
+    const bool act = co < p.Cy;
+    float acc[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] = 0.f;
+    for (long long q = p_begin + py; q < p_end; q += kPY) {
+        if (!act) continue;
+        const int w = (int)(q % p.W);
+        const int h = (int)((q / p.W) % p.H);
+        const float g = __ldg(p.dy + q * p.Cy + co);
+#pragma unroll
+        for (int tap = 0; tap < NTAPS; ++tap) {
+            int dyo = 0, dxo = 0;
+            if (NTAPS == 9) {
+                dyo = tap / 3 - 1;
+                dxo = tap % 3 - 1;
+            }
+            const int hh = h + dyo, ww = w + dxo;
+            if (hh < 0 || hh >= p.H || ww < 0 || ww >= p.W) continue;
+            const float* xs = p.x + (q + (long long)dyo * p.W + dxo) * CX;
+#pragma unroll
+            for (int ci = 0; ci < CX; ++ci) acc[tap * CX + ci] = fmaf(__ldg(xs + ci), g, acc[tap * CX + ci]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) red[(py * K + k) * blockDim.x + co] = acc[k];
+    __syncthreads();
+    if (py == 0 && act) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            float s = 0.f;
+#pragma unroll
+            for (int y = 0; y < kPY; ++y) s += red[(y * K + k) * blockDim.x + co];
+            // k = tap*CX + ci  ->  partial[split][tap][ci][co]
+            p.partial[((size_t)split * K + k) * p.Cy + co] = s;
+        }
+    }
+}
+
 }  // namespace
 
 int simt_conv_launch(const ConvProblem& p, cudaStream_t stream) {
     SINDDM_REQUIRE(p.ntaps == 9 || p.ntaps == 1, "simt_conv: ntaps must be 9 or 1");
     SINDDM_REQUIRE(p.N >= 1 && p.Cin >= 1, "simt_conv: bad channel counts");
+    const long long P = (long long)p.B * p.H * p.W;
+    if (p.Cin == 3 && p.in_res == nullptr && p.N <= 512) {
+        const size_t smem = (size_t)p.ntaps * 3 * ((p.N + 3) & ~3) * sizeof(float);
+        const unsigned blocks = (unsigned)((P + 127) / 128);
+        if (p.ntaps == 9)
+            simt_conv_smallcin_kernel<9, 3><<<blocks, 128, smem, stream>>>(p);
+        else
+            simt_conv_smallcin_kernel<1, 3><<<blocks, 128, smem, stream>>>(p);
+        SINDDM_CUDA_OK(cudaGetLastError());
+        return SINDDM_OK;
+    }
+    if (p.N <= 4 && p.Cin % 4 == 0 && p.in_res == nullptr && p.ntaps * p.Cin * 16 <= 48 * 1024 && !p.ep.w_final &&
+        !p.ep.x3) {
+        const size_t smem = (size_t)p.ntaps * p.Cin * 4 * sizeof(float);
+        simt_conv_smalln_kernel<<<(unsigned)((P + 127) / 128), 128, smem, stream>>>(p);
+        SINDDM_CUDA_OK(cudaGetLastError());
+        return SINDDM_OK;
+    }
     const int tiles_w = ceil_div(p.W, kTW), tiles_h = ceil_div(p.H, kTH);
     const int ntiles = tiles_w * tiles_h * p.B;
     simt_conv_kernel<<<ntiles, kTH * kTW, 0, stream>>>(p, tiles_w, tiles_h);
@@ -239,6 +440,15 @@ int simt_wgrad_launch(const WgradProblem& p, cudaStream_t stream) {
     const int tx = (int)align_up((size_t)p.Cy, 32);
     SINDDM_REQUIRE(tx * kPY <= 1024, "simt_wgrad: Cy=%d too large", p.Cy);
     dim3 block(tx, kPY);
+    if (p.Cx == 3 && (size_t)kPY * p.ntaps * 3 * tx * sizeof(float) <= 48 * 1024) {
+        const size_t smem = (size_t)kPY * p.ntaps * 3 * tx * sizeof(float);
+        if (p.ntaps == 9)
+            simt_wgrad_smallcx_kernel<9, 3><<<p.nsplit, block, smem, stream>>>(p);
+        else
+            simt_wgrad_smallcx_kernel<1, 3><<<p.nsplit, block, smem, stream>>>(p);
+        SINDDM_CUDA_OK(cudaGetLastError());
+        return SINDDM_OK;
+    }
     simt_wgrad_kernel<<<grid, block, (size_t)kPY * kCB * tx * sizeof(float), stream>>>(p);
     SINDDM_CUDA_OK(cudaGetLastError());
     return SINDDM_OK;
