@@ -118,6 +118,33 @@ SINDDM_DEVINL void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t*
         : "memory");
 }
 
+// Multicast variant: the box is written at the same CTA-relative smem offset of every CTA in `cta_mask`
+// and completes bytes on the mbarrier at the same offset in each of them.
+SINDDM_DEVINL void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                  uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], "
+        "[%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+        : "memory");
+}
+
+// ----------------------------------------------------------------------------------------------
+// thread-block clusters
+// ----------------------------------------------------------------------------------------------
+
+SINDDM_DEVINL uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+
+// all threads of all CTAs in the cluster
+SINDDM_DEVINL void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // ----------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation, MMA issue, commit, TMEM -> register loads
 // ----------------------------------------------------------------------------------------------
@@ -156,6 +183,16 @@ SINDDM_DEVINL void umma_tf32_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_
 SINDDM_DEVINL void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
+}
+
+// Same, arriving on the mbarrier at this CTA-relative offset in every CTA of `cta_mask` (used when the smem
+// stage being released is also written by the peers' multicast TMA).
+SINDDM_DEVINL void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"(cta_mask)
+        : "memory");
 }
 
 // 32 lanes x 16 consecutive 32-bit columns: thread i of the warp receives lane (base_lane + i).

@@ -17,9 +17,11 @@ namespace {
 
 constexpr int kSeg = 64;  // pixels per row segment
 
+constexpr int kRing = 8;  // window ring: 5 live columns + 3 columns of load-ahead (hides L2 latency)
+
 struct RowWindow {
-    // win[ky][slot]: slot = image column modulo 5
-    float v[5][5];
+    // v[ky][slot]: slot = (image column - first column) modulo kRing
+    float v[5][kRing];
 };
 
 // loads column `col` of the 5 input rows around h into slot (col mod 5); zero outside the image
@@ -42,23 +44,23 @@ SINDDM_DEVINL void slide_row(const float* __restrict__ in, int b, int h, int w0,
         rowp[ky] = in + (((size_t)b * H + (rowok[ky] ? hh : 0)) * W) * C + c;
     }
     RowWindow win;
-    // columns w0-2 .. w0+1 are needed before the first output; slots are (column + 10) % 5
+    // output column wo = w0 + i reads image columns base+i .. base+i+4 (base = w0 - 2) = slots (i + kx) % kRing;
+    // columns base .. base+6 are loaded up front, iteration i loads column base+i+7 (needed 3 outputs later)
     const int base = w0 - 2;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) load_column(win, rowp, rowok, base + j, W, C, j);
-    // process 5 outputs per outer iteration so window slots are compile-time constants
-    for (int w = w0; w < w1; w += 5) {
+    for (int j = 0; j < kRing - 1; ++j) load_column(win, rowp, rowok, base + j, W, C, j);
+    // kRing outputs per outer iteration so ring slots are compile-time constants
+    for (int w = w0; w < w1; w += kRing) {
 #pragma unroll
-        for (int j = 0; j < 5; ++j) {
+        for (int j = 0; j < kRing; ++j) {
             const int wo = w + j;
             if (wo < w1) {
-                // new column wo+2 -> slot (4 + j) % 5 ; taps kx=0..4 read slots (j + kx) % 5
-                load_column(win, rowp, rowok, wo + 2, W, C, (4 + j) % 5);
+                load_column(win, rowp, rowok, wo + 5, W, C, (j + kRing - 1) % kRing);
                 float x[5][5];
 #pragma unroll
                 for (int ky = 0; ky < 5; ++ky)
 #pragma unroll
-                    for (int kx = 0; kx < 5; ++kx) x[ky][kx] = win.v[ky][(j + kx) % 5];
+                    for (int kx = 0; kx < 5; ++kx) x[ky][kx] = win.v[ky][(j + kx) % kRing];
                 body(wo, x);
             }
         }

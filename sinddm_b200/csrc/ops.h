@@ -51,6 +51,7 @@ struct TcConvOp {
     ConvProblem p;
     int stage_bytes, nstages, smem_bytes;
     int tiles_w, tiles_h, ntiles, grid;
+    int cs;   // cluster size (CTAs sharing each weight stage through TMA multicast)
 };
 bool tc_conv_supported(const ConvProblem& p);
 int tc_conv_prepare(const ConvProblem& p, TcConvOp* op);

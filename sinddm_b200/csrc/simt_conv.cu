@@ -287,10 +287,53 @@ simt_conv_smallcin_kernel(const ConvProblem p) {
             acc.z = fmaf(xin[k], wv.z, acc.z);
             acc.w = fmaf(xin[k], wv.w, acc.w);
         }
-        const float v[4] = {acc.x, acc.y, acc.z, acc.w};
+        float v[4] = {acc.x, acc.y, acc.z, acc.w};
+        if ((N & 3) == 0) {
+            // vector epilogue: one 16-byte store per output tensor instead of four scattered 4-byte stores
+            const ConvEpilogue& ep = p.ep;
+            const size_t off = (size_t)pix * N + n0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (n0 + j < N) conv_epilogue_one(p.ep, v[j], n0 + j, N, (size_t)pix, x3v, fin);
+            for (int j = 0; j < 4; ++j) {
+                if (ep.bias) v[j] += ep.bias[n0 + j];
+                if (ep.w_res3) {
+                    const float* wr = ep.w_res3 + (n0 + j) * 3;
+                    v[j] = fmaf(x3v[2], wr[2], fmaf(x3v[1], wr[1], fmaf(x3v[0], wr[0], v[j])));
+                }
+            }
+            if (ep.res_add) {
+                const float4 r = __ldg(reinterpret_cast<const float4*>(ep.res_add + off));
+                v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
+            }
+            if (ep.out_pre) *reinterpret_cast<float4*>(ep.out_pre + off) = make_float4(v[0], v[1], v[2], v[3]);
+            if (ep.gelu) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] = gelu_erf(v[j]);
+            }
+            if (ep.dgelu_z) {
+                const float4 z = __ldg(reinterpret_cast<const float4*>(ep.dgelu_z + off));
+                v[0] *= gelu_erf_grad(z.x); v[1] *= gelu_erf_grad(z.y);
+                v[2] *= gelu_erf_grad(z.z); v[3] *= gelu_erf_grad(z.w);
+            }
+            if (ep.w_final) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    fin[0] = fmaf(v[j], ep.w_final[0 * N + n0 + j], fin[0]);
+                    fin[1] = fmaf(v[j], ep.w_final[1 * N + n0 + j], fin[1]);
+                    fin[2] = fmaf(v[j], ep.w_final[2 * N + n0 + j], fin[2]);
+                }
+            }
+            if (ep.out) {
+                if (ep.round_tf32) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) v[j] = round_tf32(v[j]);
+                }
+                *reinterpret_cast<float4*>(ep.out + off) = make_float4(v[0], v[1], v[2], v[3]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (n0 + j < N) conv_epilogue_one(p.ep, v[j], n0 + j, N, (size_t)pix, x3v, fin);
+        }
     }
     if (p.ep.w_final) {
         const size_t plane = (size_t)p.H * p.W;

@@ -17,6 +17,9 @@
 //   roles          warp 0: TMA producer (one lane) | warp 1: TMEM alloc + MMA issue (one lane)
 //                  warps 2-5: epilogue (TMEM -> registers -> bias/residual/GELU/... -> global)
 //   grid           persistent, min(#tiles, #SMs) CTAs, static round-robin over tiles.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 #include "ops.h"
 
@@ -42,6 +45,9 @@ struct KernelArgs {
     int N;
     int tiles_w, tiles_h, ntiles;
     int nstages, stage_bytes;
+    int cs;                    // cluster size: CTAs of a cluster work on cs different tiles and share every
+    int b_rows;                // weight stage -- each loads N/cs rows of it and multicasts them to all
+    int nsuper;                // ceil(ntiles / cs)
     uint32_t idesc;
     ConvEpilogue ep;
 };
@@ -83,7 +89,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         }
         for (int i = 0; i < a.nstages; ++i) {
             mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], 1);
+            mbar_init(&empty_bar[i], a.cs);   // every CTA of the cluster releases the stage
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
@@ -106,8 +112,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     }
     tc_fence_before_sync();
     __syncthreads();
+    if (a.cs > 1) cluster_sync_all();   // peers' barriers are initialised before any multicast / remote arrive
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    const int crank = a.cs > 1 ? (int)cluster_ctarank() : 0;
+    const int cluster_id = blockIdx.x / a.cs;
+    const int nclusters = gridDim.x / a.cs;
+    const uint16_t cmask = (uint16_t)((1u << a.cs) - 1u);
 
     const int nk_main = a.nchunks * a.ntaps;
     const int nk = nk_main + a.nchunks_res;
@@ -118,7 +129,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+            for (int st = cluster_id; st < a.nsuper; st += nclusters) {
+                // tiles past the end (ragged last cluster) run the same pipeline on an all-zero tile:
+                // image index B is out of bounds for TMA, which zero-fills the box
+                const int tile = st * a.cs + crank;
                 const int tw = tile % a.tiles_w;
                 const int th = (tile / a.tiles_w) % a.tiles_h;
                 const int b = tile / (a.tiles_w * a.tiles_h);
@@ -137,11 +151,19 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                             dx = tap % 3 - 1;
                         }
                         tma_load_4d(sa, &tm_a, &full_bar[stage], c * kKC, w0 + dx, h0 + dy, b);
-                        tma_load_2d(sb, &tm_b, &full_bar[stage], c * kKC, tap * N);
+                        if (a.cs == 1)
+                            tma_load_2d(sb, &tm_b, &full_bar[stage], c * kKC, tap * N);
+                        else
+                            tma_load_2d_mc(sb + (size_t)crank * a.b_rows * (kKC * 4), &tm_b, &full_bar[stage], c * kKC,
+                                           tap * N + crank * a.b_rows, cmask);
                     } else {
                         const int c = it - nk_main;
                         tma_load_4d(sa, &tm_ares, &full_bar[stage], c * kKC, w0, h0, b);
-                        tma_load_2d(sb, &tm_bres, &full_bar[stage], c * kKC, 0);
+                        if (a.cs == 1)
+                            tma_load_2d(sb, &tm_bres, &full_bar[stage], c * kKC, 0);
+                        else
+                            tma_load_2d_mc(sb + (size_t)crank * a.b_rows * (kKC * 4), &tm_bres, &full_bar[stage],
+                                           c * kKC, crank * a.b_rows, cmask);
                     }
                     if (++stage == a.nstages) {
                         stage = 0;
@@ -157,7 +179,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             int stage = 0;
             uint32_t phase = 0;
             int titer = 0;
-            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++titer) {
+            for (int st = cluster_id; st < a.nsuper; st += nclusters, ++titer) {
                 const int buf = titer & 1;
                 mbar_wait(&tempty_bar[buf], (((uint32_t)titer >> 1) & 1u) ^ 1u);
                 tc_fence_after_sync();
@@ -180,7 +202,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                         const uint64_t db = umma_smem_desc(sb + k * 32, 0, 1024, UMMA_LAYOUT_SW128);
                         umma_tf32_ss(d_tmem, da, db, a.idesc, (it | k) != 0 ? 1u : 0u);
                     }
-                    umma_commit(&empty_bar[stage]);
+                    if (a.cs == 1)
+                        umma_commit(&empty_bar[stage]);
+                    else
+                        umma_commit_mc(&empty_bar[stage], cmask);
                     if (++stage == a.nstages) {
                         stage = 0;
                         phase ^= 1u;
@@ -197,12 +222,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         const int hl = row / kTileW, wl = row % kTileW;
         const ConvEpilogue& ep = a.ep;
         int titer = 0;
-        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++titer) {
+        for (int st = cluster_id; st < a.nsuper; st += nclusters, ++titer) {
+            const int tile = st * a.cs + crank;
             const int tw = tile % a.tiles_w;
             const int th = (tile / a.tiles_w) % a.tiles_h;
             const int b = tile / (a.tiles_w * a.tiles_h);
             const int h = th * kTileH + hl, w = tw * kTileW + wl;
-            const bool valid = (h < a.H) && (w < a.W);
+            const bool valid = (tile < a.ntiles) && (h < a.H) && (w < a.W);
             const size_t pix = ((size_t)b * a.H + h) * a.W + w;
             const int buf = titer & 1;
 
@@ -301,6 +327,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     // ---------------------------------------------------------------- teardown
     tc_fence_before_sync();
     __syncthreads();
+    if (a.cs > 1) cluster_sync_all();   // nobody exits while a peer may still multicast into its smem
     if (warp == 1) {
         tc_fence_after_sync();
         tmem_dealloc(tmem_base, kTmemCols);
@@ -308,6 +335,17 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 }
 
 }  // namespace
+
+// SINDDM_TC_CLUSTER = 1 | 2 | 4 (default 2): CTAs per cluster sharing each weight stage by TMA multicast
+static int cluster_size_setting() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SINDDM_TC_CLUSTER");
+        v = e ? atoi(e) : 2;
+        if (v != 1 && v != 2 && v != 4) v = 2;
+    }
+    return v;
+}
 
 bool tc_conv_supported(const ConvProblem& p) {
     if (p.Cin < 8 || p.Cin % 8 != 0) return false;
@@ -323,11 +361,15 @@ int tc_conv_prepare(const ConvProblem& p, TcConvOp* op) {
     SINDDM_REQUIRE(device_info().initialized, "sinddm_init() has not been called");
     op->p = p;
     SINDDM_TRY(make_tmap_nhwc(&op->tm_a, p.in, p.B, p.H, p.W, p.Cin, kKC, kTileW, kTileH, CU_TENSOR_MAP_SWIZZLE_128B));
-    SINDDM_TRY(make_tmap_2d(&op->tm_b, p.w, p.Cin, p.ntaps * p.N, kKC, p.N, CU_TENSOR_MAP_SWIZZLE_128B));
+    // cluster size: weight slices must be whole 8-row (1024 B) swizzle atoms
+    int cs = cluster_size_setting();
+    while (cs > 1 && (p.N % (8 * cs) != 0)) cs >>= 1;
+    op->cs = cs;
+    SINDDM_TRY(make_tmap_2d(&op->tm_b, p.w, p.Cin, p.ntaps * p.N, kKC, p.N / cs, CU_TENSOR_MAP_SWIZZLE_128B));
     if (p.in_res) {
         SINDDM_TRY(make_tmap_nhwc(&op->tm_ares, p.in_res, p.B, p.H, p.W, p.Cres, kKC, kTileW, kTileH,
                                   CU_TENSOR_MAP_SWIZZLE_128B));
-        SINDDM_TRY(make_tmap_2d(&op->tm_bres, p.w_res, p.Cres, p.N, kKC, p.N, CU_TENSOR_MAP_SWIZZLE_128B));
+        SINDDM_TRY(make_tmap_2d(&op->tm_bres, p.w_res, p.Cres, p.N, kKC, p.N / cs, CU_TENSOR_MAP_SWIZZLE_128B));
     } else {
         op->tm_ares = op->tm_a;
         op->tm_bres = op->tm_b;
@@ -342,7 +384,10 @@ int tc_conv_prepare(const ConvProblem& p, TcConvOp* op) {
     op->tiles_w = ceil_div(p.W, kTileW);
     op->tiles_h = ceil_div(p.H, kTileH);
     op->ntiles = op->tiles_w * op->tiles_h * p.B;
-    op->grid = op->ntiles < device_info().num_sms ? op->ntiles : device_info().num_sms;
+    const int nsuper = ceil_div(op->ntiles, cs);
+    int nclusters = device_info().num_sms / cs;
+    if (nclusters > nsuper) nclusters = nsuper;
+    op->grid = nclusters * cs;
     return SINDDM_OK;
 }
 
@@ -373,7 +418,23 @@ int tc_conv_launch(const TcConvOp& op, cudaStream_t stream) {
     a.ep = p.ep;
     // algorithmic work: real pixels x N x (taps*Cin + Cres) MACs
     prof_begin(stream, 0, 2.0 * (double)p.B * p.H * p.W * p.N * ((double)p.ntaps * p.Cin + a.Cres));
-    tc_conv_kernel<<<op.grid, kThreads, op.smem_bytes, stream>>>(op.tm_a, op.tm_ares, op.tm_b, op.tm_bres, a);
+    a.cs = op.cs;
+    a.b_rows = p.N / op.cs;
+    a.nsuper = ceil_div(op.ntiles, op.cs);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(op.grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = op.smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = op.cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SINDDM_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_conv_kernel, op.tm_a, op.tm_ares, op.tm_b, op.tm_bres, a));
     prof_end(stream);
     SINDDM_CUDA_OK(cudaGetLastError());
     return SINDDM_OK;
