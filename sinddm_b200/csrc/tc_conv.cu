@@ -3,17 +3,23 @@
 // Replaces the cuDNN implicit-GEMM calls behind nn.Conv2d in SinDDMConvBlock.net / res_conv
 // (reference SinDDM/models.py:62-67,79-80) and, with data-gradient-packed weights, their backward.
 //
-//   GEMM view      M = pixels (tile = 8 rows x 16 cols = 128 pixels of one image)
+//   GEMM view      M = pixels: one CTA tile = 16 rows x 16 cols of one image = two UMMA M=128 halves
 //                  N = output channels (one UMMA N, 16..160)
-//                  K = taps x input channels, walked as (32-channel chunk, tap) steps;
-//                      an optional 1x1 residual conv rides along as extra K steps from a second input.
-//   A operand      NHWC activations.  Each K step is ONE 4-D TMA box (32 ch, 16 w, 8 h, 1 b) whose
-//                  start coordinate is shifted by the tap offset; the halo and the image border are
-//                  out-of-bounds coordinates that TMA zero-fills, i.e. exact zero padding, no im2col.
-//   B operand      packed weights [tap][N][Cin] (K-major), one 2-D TMA box (32 ch, N rows) per step.
-//   both land in 128B-swizzled K-major smem tiles that the UMMA descriptors consume directly.
-//   accumulator    fp32 in TMEM, double buffered (2 x 256 columns) so the epilogue of tile i overlaps
-//                  the main loop of tile i+1.
+//                  K = taps x input channels (+ an optional 1x1 residual conv as extra K from a second input)
+//
+// With fp32 (TF32) operands the kernel is bound by how many bytes the TMA unit can bring into shared memory
+// (measured ~32 B/cycle/SM, profiles/), not by the tensor pipe, so the K walk is arranged for operand reuse
+// INSIDE shared memory:
+//   * one pipeline stage = (32-channel chunk c, horizontal tap kx).  Its A box is the (16+2) x 16 pixel halo
+//     tile shifted by kx-1 columns (4-D TMA box (32 ch, 16 w, 18 h, 1 b); out-of-image pixels and the channel
+//     tail are zero-filled by TMA = exact zero padding, no im2col buffer).  The three vertical taps ky and
+//     the two M halves are just different 2 KiB-aligned row offsets into that one box:
+//         A(ky, half) = box + (ky + 8*half) * 16 px * 128 B
+//     so every loaded activation byte feeds 3 taps, and every weight byte (3 boxes [N][32] per stage) feeds
+//     256 pixels: 2.3x fewer bytes per FLOP than a tap-by-tap 128-pixel walk.
+//   * operands land in 128B-swizzled K-major tiles that the UMMA descriptors consume directly.
+//   accumulators   fp32 in TMEM: three slots of N columns; tile pair p uses slots (2p, 2p+1) mod 3, so the
+//                  main loop of pair p+1 only waits for the epilogue of the FIRST half of pair p.
 //   roles          warp 0: TMA producer (one lane) | warp 1: TMEM alloc + MMA issue (one lane)
 //                  warps 2-5: epilogue (TMEM -> registers -> bias/residual/GELU/... -> global)
 //   grid           persistent, min(#tiles, #SMs) CTAs, static round-robin over tiles.
@@ -27,35 +33,35 @@ namespace sinddm {
 
 namespace {
 
-constexpr int kTileH = 8;
+constexpr int kTileH = 16;
 constexpr int kTileW = 16;
-constexpr int kBM = kTileH * kTileW;      // 128 rows = UMMA M
-constexpr int kKC = 32;                   // channels per K step (32 fp32 = one 128B swizzle row)
-constexpr int kABytes = kBM * kKC * 4;    // 16 KiB
+constexpr int kBoxH = kTileH + 2;            // halo rows
+constexpr int kKC = 32;                      // channels per K chunk (32 fp32 = one 128B swizzle row)
+constexpr int kRowBytes = kTileW * kKC * 4;  // one image row of the box: 16 px x 128 B = 2 KiB
+constexpr int kABytes = kBoxH * kRowBytes;   // 36 KiB
 constexpr int kMaxN = 160;
 constexpr int kThreads = 192;
 constexpr int kEpiThreads = 128;
 constexpr int kTmemCols = 512;
-constexpr int kAccStride = 256;           // TMEM column offset between the two accumulator buffers
+constexpr int kSlots = 3;
+constexpr int kMaxStages = 4;
 
 struct KernelArgs {
     int B, H, W;
-    int Cin, ntaps, nchunks;   // main K walk: nchunks x ntaps steps
-    int Cres, nchunks_res;     // residual K walk: nchunks_res steps (center tap)
+    int Cin, ntaps, nchunks;   // main K walk: nchunks x (3 or 1) stages
+    int Cres, nchunks_res;     // residual K walk: nchunks_res stages (centre tap only)
     int N;
     int tiles_w, tiles_h, ntiles;
     int nstages, stage_bytes;
-    int cs;                    // cluster size: CTAs of a cluster work on cs different tiles and share every
-    int b_rows;                // weight stage -- each loads N/cs rows of it and multicasts them to all
-    int nsuper;                // ceil(ntiles / cs)
+    int slot_stride;           // TMEM columns between accumulator slots
     uint32_t idesc;
     ConvEpilogue ep;
 };
 
-// smem carve-up (after the 1024-aligned stage ring):
-//   uint64 full[nstages], empty[nstages], tmem_full[2], tmem_empty[2]; uint32 tmem_slot;
+// smem tail (after the 1024-aligned stage ring):
+//   uint64 full[4], empty[4], tfull[3], tempty[3]; uint32 tmem_slot[4];
 //   float bias[kMaxN], wres3[kMaxN*3], wfinal[3*kMaxN], bfinal[4]
-constexpr int kTailBytes = 16 * 8 * 2 + 4 * 8 + 16 + (kMaxN + kMaxN * 3 + 3 * kMaxN + 4) * 4;
+constexpr int kTailBytes = (2 * kMaxStages + 2 * kSlots) * 8 + 16 + (kMaxN + kMaxN * 3 + 3 * kMaxN + 4) * 4 + 64;
 
 __global__ void __launch_bounds__(kThreads, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_ares,
@@ -66,10 +72,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 
     uint8_t* tail = smem + (size_t)a.nstages * a.stage_bytes;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
-    uint64_t* empty_bar = full_bar + 16;
-    uint64_t* tfull_bar = empty_bar + 16;
-    uint64_t* tempty_bar = tfull_bar + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    uint64_t* empty_bar = full_bar + kMaxStages;
+    uint64_t* tfull_bar = empty_bar + kMaxStages;
+    uint64_t* tempty_bar = tfull_bar + kSlots;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + kSlots);
     float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
     float* s_wres3 = s_bias + kMaxN;
     float* s_wfinal = s_wres3 + kMaxN * 3;
@@ -89,17 +95,15 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         }
         for (int i = 0; i < a.nstages; ++i) {
             mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], a.cs);   // every CTA of the cluster releases the stage
+            mbar_init(&empty_bar[i], 1);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kSlots; ++i) {
             mbar_init(&tfull_bar[i], 1);
             mbar_init(&tempty_bar[i], kEpiThreads);
         }
         fence_mbar_init();
     }
-    if (warp == 1) {
-        tmem_alloc(tmem_slot, kTmemCols);
-    }
+    if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
     if (warp >= 2) {
         const int t = threadIdx.x - 64;
         for (int i = t; i < N; i += kEpiThreads) s_bias[i] = a.ep.bias ? a.ep.bias[i] : 0.f;
@@ -112,58 +116,44 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (a.cs > 1) cluster_sync_all();   // peers' barriers are initialised before any multicast / remote arrive
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
-    const int crank = a.cs > 1 ? (int)cluster_ctarank() : 0;
-    const int cluster_id = blockIdx.x / a.cs;
-    const int nclusters = gridDim.x / a.cs;
-    const uint16_t cmask = (uint16_t)((1u << a.cs) - 1u);
 
-    const int nk_main = a.nchunks * a.ntaps;
-    const int nk = nk_main + a.nchunks_res;
-    const uint32_t b_bytes = (uint32_t)N * kKC * 4;
+    const int nkx = a.ntaps == 9 ? 3 : 1;           // horizontal taps = stages per chunk
+    const int nky = nkx;                             // vertical taps = weight boxes per stage
+    const int nst_main = a.nchunks * nkx;
+    const int nst = nst_main + a.nchunks_res;        // stages per tile
+    const uint32_t nbytes = (uint32_t)N * kKC * 4;   // one weight box
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int st = cluster_id; st < a.nsuper; st += nclusters) {
-                // tiles past the end (ragged last cluster) run the same pipeline on an all-zero tile:
-                // image index B is out of bounds for TMA, which zero-fills the box
-                const int tile = st * a.cs + crank;
+            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
                 const int tw = tile % a.tiles_w;
                 const int th = (tile / a.tiles_w) % a.tiles_h;
                 const int b = tile / (a.tiles_w * a.tiles_h);
                 const int h0 = th * kTileH, w0 = tw * kTileW;
-                for (int it = 0; it < nk; ++it) {
+                for (int it = 0; it < nst; ++it) {
                     mbar_wait(&empty_bar[stage], phase ^ 1u);
                     uint8_t* sa = smem + (size_t)stage * a.stage_bytes;
                     uint8_t* sb = sa + kABytes;
-                    mbar_arrive_expect_tx(&full_bar[stage], kABytes + b_bytes);
-                    if (it < nk_main) {
-                        const int c = it / a.ntaps;
-                        const int tap = it - c * a.ntaps;
-                        int dy = 0, dx = 0;
-                        if (a.ntaps == 9) {
-                            dy = tap / 3 - 1;
-                            dx = tap % 3 - 1;
+                    if (it < nst_main) {
+                        const int c = it / nkx;
+                        const int kx = it - c * nkx;
+                        mbar_arrive_expect_tx(&full_bar[stage], kABytes + (uint32_t)nky * nbytes);
+                        // rows h0-1 .. h0+16, columns shifted by the horizontal tap (centre column for 1x1)
+                        tma_load_4d(sa, &tm_a, &full_bar[stage], c * kKC, w0 + (nkx == 3 ? kx - 1 : 0), h0 - 1, b);
+                        for (int ky = 0; ky < nky; ++ky) {
+                            const int tap = nkx == 3 ? ky * 3 + kx : 0;
+                            tma_load_2d(sb + (size_t)ky * nbytes, &tm_b, &full_bar[stage], c * kKC, tap * N);
                         }
-                        tma_load_4d(sa, &tm_a, &full_bar[stage], c * kKC, w0 + dx, h0 + dy, b);
-                        if (a.cs == 1)
-                            tma_load_2d(sb, &tm_b, &full_bar[stage], c * kKC, tap * N);
-                        else
-                            tma_load_2d_mc(sb + (size_t)crank * a.b_rows * (kKC * 4), &tm_b, &full_bar[stage], c * kKC,
-                                           tap * N + crank * a.b_rows, cmask);
                     } else {
-                        const int c = it - nk_main;
-                        tma_load_4d(sa, &tm_ares, &full_bar[stage], c * kKC, w0, h0, b);
-                        if (a.cs == 1)
-                            tma_load_2d(sb, &tm_bres, &full_bar[stage], c * kKC, 0);
-                        else
-                            tma_load_2d_mc(sb + (size_t)crank * a.b_rows * (kKC * 4), &tm_bres, &full_bar[stage],
-                                           c * kKC, crank * a.b_rows, cmask);
+                        const int c = it - nst_main;
+                        mbar_arrive_expect_tx(&full_bar[stage], kABytes + nbytes);
+                        tma_load_4d(sa, &tm_ares, &full_bar[stage], c * kKC, w0, h0 - 1, b);
+                        tma_load_2d(sb, &tm_bres, &full_bar[stage], c * kKC, 0);
                     }
                     if (++stage == a.nstages) {
                         stage = 0;
@@ -178,148 +168,163 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            uint32_t slot_uses[kSlots] = {0, 0, 0};
             int titer = 0;
-            for (int st = cluster_id; st < a.nsuper; st += nclusters, ++titer) {
-                const int buf = titer & 1;
-                mbar_wait(&tempty_bar[buf], (((uint32_t)titer >> 1) & 1u) ^ 1u);
+            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++titer) {
+                const int s0 = (2 * titer) % kSlots, s1 = (2 * titer + 1) % kSlots;
+                // the slot must have been drained by the epilogue of its previous use
+                mbar_wait(&tempty_bar[s0], (slot_uses[s0] & 1u) ^ 1u);
+                mbar_wait(&tempty_bar[s1], (slot_uses[s1] & 1u) ^ 1u);
+                ++slot_uses[s0];
+                ++slot_uses[s1];
                 tc_fence_after_sync();
-                const uint32_t d_tmem = tmem_base + (uint32_t)buf * kAccStride;
-                for (int it = 0; it < nk; ++it) {
+                const uint32_t d0 = tmem_base + (uint32_t)(s0 * a.slot_stride);
+                const uint32_t d1 = tmem_base + (uint32_t)(s1 * a.slot_stride);
+                for (int it = 0; it < nst; ++it) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after_sync();
                     const uint32_t sa = smem_u32(smem + (size_t)stage * a.stage_bytes);
                     const uint32_t sb = sa + kABytes;
-                    int cvalid;
-                    if (it < nk_main) {
-                        const int c = it / a.ntaps;
-                        cvalid = min(kKC, a.Cin - c * kKC);
-                    } else {
-                        cvalid = min(kKC, a.Cres - (it - nk_main) * kKC);
-                    }
+                    const bool main = it < nst_main;
+                    const int cvalid = main ? min(kKC, a.Cin - (it / nkx) * kKC) : min(kKC, a.Cres - (it - nst_main) * kKC);
                     const int nmma = cvalid >> 3;  // K = 8 tf32 per instruction
-                    for (int k = 0; k < nmma; ++k) {
-                        const uint64_t da = umma_smem_desc(sa + k * 32, 0, 1024, UMMA_LAYOUT_SW128);
-                        const uint64_t db = umma_smem_desc(sb + k * 32, 0, 1024, UMMA_LAYOUT_SW128);
-                        umma_tf32_ss(d_tmem, da, db, a.idesc, (it | k) != 0 ? 1u : 0u);
+                    const int kys = main ? nky : 1;
+                    for (int ky = 0; ky < kys; ++ky) {
+                        // vertical tap = row offset into the halo box; the 1x1 / residual case reads the centre rows
+                        const int row0 = (main && nky == 3) ? ky : 1;
+                        const uint32_t a0 = sa + (uint32_t)row0 * kRowBytes;
+                        const uint32_t a1 = a0 + 8u * kRowBytes;
+                        const uint32_t bb = sb + (uint32_t)ky * nbytes;
+                        for (int k = 0; k < nmma; ++k) {
+                            const uint32_t acc = (it | ky | k) != 0 ? 1u : 0u;
+                            const uint64_t db = umma_smem_desc(bb + k * 32, 0, 1024, UMMA_LAYOUT_SW128);
+                            umma_tf32_ss(d0, umma_smem_desc(a0 + k * 32, 0, 1024, UMMA_LAYOUT_SW128), db, a.idesc, acc);
+                            umma_tf32_ss(d1, umma_smem_desc(a1 + k * 32, 0, 1024, UMMA_LAYOUT_SW128), db, a.idesc, acc);
+                        }
                     }
-                    if (a.cs == 1)
-                        umma_commit(&empty_bar[stage]);
-                    else
-                        umma_commit_mc(&empty_bar[stage], cmask);
+                    umma_commit(&empty_bar[stage]);
                     if (++stage == a.nstages) {
                         stage = 0;
                         phase ^= 1u;
                     }
                 }
-                umma_commit(&tfull_bar[buf]);
+                umma_commit(&tfull_bar[s0]);
+                umma_commit(&tfull_bar[s1]);
             }
         }
         __syncwarp();
     } else {
         // ------------------------------------------------------------ epilogue warps
         const int quarter = warp & 3;             // TMEM lane quarter this warp may read
-        const int row = quarter * 32 + lane;      // accumulator row == pixel within the tile
-        const int hl = row / kTileW, wl = row % kTileW;
+        const int row = quarter * 32 + lane;      // accumulator row == pixel within the half tile
         const ConvEpilogue& ep = a.ep;
+        uint32_t slot_uses[kSlots] = {0, 0, 0};
         int titer = 0;
-        for (int st = cluster_id; st < a.nsuper; st += nclusters, ++titer) {
-            const int tile = st * a.cs + crank;
+        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++titer) {
             const int tw = tile % a.tiles_w;
             const int th = (tile / a.tiles_w) % a.tiles_h;
             const int b = tile / (a.tiles_w * a.tiles_h);
-            const int h = th * kTileH + hl, w = tw * kTileW + wl;
-            const bool valid = (tile < a.ntiles) && (h < a.H) && (w < a.W);
-            const size_t pix = ((size_t)b * a.H + h) * a.W + w;
-            const int buf = titer & 1;
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                const int slot = (2 * titer + half) % kSlots;
+                const int h = th * kTileH + half * 8 + row / kTileW, w = tw * kTileW + row % kTileW;
+                const bool valid = (h < a.H) && (w < a.W);
+                const size_t pix = ((size_t)b * a.H + h) * a.W + w;
 
-            float x3v[3] = {0.f, 0.f, 0.f};
-            if (ep.x3 && valid) {
-                x3v[0] = ep.x3[pix * 3 + 0];
-                x3v[1] = ep.x3[pix * 3 + 1];
-                x3v[2] = ep.x3[pix * 3 + 2];
-            }
-            float fin[3] = {0.f, 0.f, 0.f};
-
-            mbar_wait(&tfull_bar[buf], ((uint32_t)titer >> 1) & 1u);
-            tc_fence_after_sync();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)buf * kAccStride;
-
-            for (int cc = 0; cc < N; cc += 16) {
-                float v[16];
-                tmem_ld16(taddr + cc, v);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] += s_bias[cc + j];
-                if (ep.w_res3) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float* wr = &s_wres3[(cc + j) * 3];
-                        v[j] = fmaf(x3v[2], wr[2], fmaf(x3v[1], wr[1], fmaf(x3v[0], wr[0], v[j])));
-                    }
+                float x3v[3] = {0.f, 0.f, 0.f};
+                if (ep.x3 && valid) {
+                    x3v[0] = ep.x3[pix * 3 + 0];
+                    x3v[1] = ep.x3[pix * 3 + 1];
+                    x3v[2] = ep.x3[pix * 3 + 2];
                 }
-                if (valid) {
-                    const size_t off = pix * N + cc;
-                    if (ep.res_add) {
-                        const float4* r4 = reinterpret_cast<const float4*>(ep.res_add + off);
+                float fin[3] = {0.f, 0.f, 0.f};
+
+                mbar_wait(&tfull_bar[slot], slot_uses[slot] & 1u);
+                ++slot_uses[slot];
+                tc_fence_after_sync();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(slot * a.slot_stride);
+
+                for (int cc = 0; cc < N; cc += 16) {
+                    float v[16];
+                    tmem_ld16(taddr + cc, v);
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const float4 r = __ldg(r4 + q);
-                            v[4 * q + 0] += r.x;
-                            v[4 * q + 1] += r.y;
-                            v[4 * q + 2] += r.z;
-                            v[4 * q + 3] += r.w;
-                        }
-                    }
-                    if (ep.out_pre) {
-                        float4* o4 = reinterpret_cast<float4*>(ep.out_pre + off);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            o4[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                    }
-                    if (ep.gelu) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
-                    }
-                    if (ep.dgelu_z) {
-                        const float4* z4 = reinterpret_cast<const float4*>(ep.dgelu_z + off);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const float4 z = __ldg(z4 + q);
-                            v[4 * q + 0] *= gelu_erf_grad(z.x);
-                            v[4 * q + 1] *= gelu_erf_grad(z.y);
-                            v[4 * q + 2] *= gelu_erf_grad(z.z);
-                            v[4 * q + 3] *= gelu_erf_grad(z.w);
-                        }
-                    }
-                    if (ep.w_final) {
+                    for (int j = 0; j < 16; ++j) v[j] += s_bias[cc + j];
+                    if (ep.w_res3) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            fin[0] = fmaf(v[j], s_wfinal[0 * N + cc + j], fin[0]);
-                            fin[1] = fmaf(v[j], s_wfinal[1 * N + cc + j], fin[1]);
-                            fin[2] = fmaf(v[j], s_wfinal[2 * N + cc + j], fin[2]);
+                            const float* wr = &s_wres3[(cc + j) * 3];
+                            v[j] = fmaf(x3v[2], wr[2], fmaf(x3v[1], wr[1], fmaf(x3v[0], wr[0], v[j])));
                         }
                     }
-                    if (ep.out) {
-                        if (ep.round_tf32) {
+                    if (valid) {
+                        const size_t off = pix * N + cc;
+                        if (ep.res_add) {
+                            const float4* r4 = reinterpret_cast<const float4*>(ep.res_add + off);
+                            float4 r[4];
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) v[j] = round_tf32(v[j]);
+                            for (int q = 0; q < 4; ++q) r[q] = __ldg(r4 + q);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                v[4 * q + 0] += r[q].x;
+                                v[4 * q + 1] += r[q].y;
+                                v[4 * q + 2] += r[q].z;
+                                v[4 * q + 3] += r[q].w;
+                            }
                         }
-                        float4* o4 = reinterpret_cast<float4*>(ep.out + off);
+                        if (ep.out_pre) {
+                            float4* o4 = reinterpret_cast<float4*>(ep.out_pre + off);
 #pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            o4[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                            for (int q = 0; q < 4; ++q)
+                                o4[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                        }
+                        if (ep.gelu) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
+                        }
+                        if (ep.dgelu_z) {
+                            const float4* z4 = reinterpret_cast<const float4*>(ep.dgelu_z + off);
+                            float4 z[4];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) z[q] = __ldg(z4 + q);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                v[4 * q + 0] *= gelu_erf_grad(z[q].x);
+                                v[4 * q + 1] *= gelu_erf_grad(z[q].y);
+                                v[4 * q + 2] *= gelu_erf_grad(z[q].z);
+                                v[4 * q + 3] *= gelu_erf_grad(z[q].w);
+                            }
+                        }
+                        if (ep.w_final) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                fin[0] = fmaf(v[j], s_wfinal[0 * N + cc + j], fin[0]);
+                                fin[1] = fmaf(v[j], s_wfinal[1 * N + cc + j], fin[1]);
+                                fin[2] = fmaf(v[j], s_wfinal[2 * N + cc + j], fin[2]);
+                            }
+                        }
+                        if (ep.out) {
+                            if (ep.round_tf32) {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) v[j] = round_tf32(v[j]);
+                            }
+                            float4* o4 = reinterpret_cast<float4*>(ep.out + off);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                o4[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                        }
                     }
                 }
-            }
-            // every tcgen05.ld of this buffer has completed (wait::ld inside tmem_ld16): hand it back
-            tc_fence_before_sync();
-            mbar_arrive(&tempty_bar[buf]);
+                // every tcgen05.ld of this slot has completed (wait::ld inside tmem_ld16): hand it back
+                tc_fence_before_sync();
+                mbar_arrive(&tempty_bar[slot]);
 
-            if (ep.w_final && valid) {
-                const size_t plane = (size_t)a.H * a.W;
-                float* o = ep.out_final + (size_t)b * 3 * plane + (size_t)h * a.W + w;
-                o[0] = fin[0] + s_bfinal[0];
-                o[plane] = fin[1] + s_bfinal[1];
-                o[2 * plane] = fin[2] + s_bfinal[2];
+                if (ep.w_final && valid) {
+                    const size_t plane = (size_t)a.H * a.W;
+                    float* o = ep.out_final + (size_t)b * 3 * plane + (size_t)h * a.W + w;
+                    o[0] = fin[0] + s_bfinal[0];
+                    o[plane] = fin[1] + s_bfinal[1];
+                    o[2 * plane] = fin[2] + s_bfinal[2];
+                }
             }
         }
     }
@@ -327,7 +332,6 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     // ---------------------------------------------------------------- teardown
     tc_fence_before_sync();
     __syncthreads();
-    if (a.cs > 1) cluster_sync_all();   // nobody exits while a peer may still multicast into its smem
     if (warp == 1) {
         tc_fence_after_sync();
         tmem_dealloc(tmem_base, kTmemCols);
@@ -335,17 +339,6 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 }
 
 }  // namespace
-
-// SINDDM_TC_CLUSTER = 1 | 2 | 4 (default 2): CTAs per cluster sharing each weight stage by TMA multicast
-static int cluster_size_setting() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("SINDDM_TC_CLUSTER");
-        v = e ? atoi(e) : 2;
-        if (v != 1 && v != 2 && v != 4) v = 2;
-    }
-    return v;
-}
 
 bool tc_conv_supported(const ConvProblem& p) {
     if (p.Cin < 8 || p.Cin % 8 != 0) return false;
@@ -360,43 +353,38 @@ int tc_conv_prepare(const ConvProblem& p, TcConvOp* op) {
                    p.N, p.ntaps);
     SINDDM_REQUIRE(device_info().initialized, "sinddm_init() has not been called");
     op->p = p;
-    SINDDM_TRY(make_tmap_nhwc(&op->tm_a, p.in, p.B, p.H, p.W, p.Cin, kKC, kTileW, kTileH, CU_TENSOR_MAP_SWIZZLE_128B));
-    // cluster size: weight slices must be whole 8-row (1024 B) swizzle atoms
-    int cs = cluster_size_setting();
-    while (cs > 1 && (p.N % (8 * cs) != 0)) cs >>= 1;
-    op->cs = cs;
-    SINDDM_TRY(make_tmap_2d(&op->tm_b, p.w, p.Cin, p.ntaps * p.N, kKC, p.N / cs, CU_TENSOR_MAP_SWIZZLE_128B));
+    op->cs = 1;
+    SINDDM_TRY(make_tmap_nhwc(&op->tm_a, p.in, p.B, p.H, p.W, p.Cin, kKC, kTileW, kBoxH, CU_TENSOR_MAP_SWIZZLE_128B));
+    SINDDM_TRY(make_tmap_2d(&op->tm_b, p.w, p.Cin, p.ntaps * p.N, kKC, p.N, CU_TENSOR_MAP_SWIZZLE_128B));
     if (p.in_res) {
-        SINDDM_TRY(make_tmap_nhwc(&op->tm_ares, p.in_res, p.B, p.H, p.W, p.Cres, kKC, kTileW, kTileH,
+        SINDDM_TRY(make_tmap_nhwc(&op->tm_ares, p.in_res, p.B, p.H, p.W, p.Cres, kKC, kTileW, kBoxH,
                                   CU_TENSOR_MAP_SWIZZLE_128B));
-        SINDDM_TRY(make_tmap_2d(&op->tm_bres, p.w_res, p.Cres, p.N, kKC, p.N / cs, CU_TENSOR_MAP_SWIZZLE_128B));
+        SINDDM_TRY(make_tmap_2d(&op->tm_bres, p.w_res, p.Cres, p.N, kKC, p.N, CU_TENSOR_MAP_SWIZZLE_128B));
     } else {
         op->tm_ares = op->tm_a;
         op->tm_bres = op->tm_b;
     }
-    op->stage_bytes = kABytes + (int)align_up((size_t)p.N * kKC * 4, 1024);
+    const int nky = p.ntaps == 9 ? 3 : 1;
+    op->stage_bytes = kABytes + (int)align_up((size_t)nky * p.N * kKC * 4, 1024);
     const int budget = device_info().max_smem_optin - 1024 /*alignment slack*/ - kTailBytes;
     int nst = budget / op->stage_bytes;
-    if (nst > 8) nst = 8;
+    if (nst > kMaxStages) nst = kMaxStages;
     SINDDM_REQUIRE(nst >= 2, "tc_conv: not enough shared memory for a 2-stage pipeline");
     op->nstages = nst;
     op->smem_bytes = nst * op->stage_bytes + kTailBytes + 1024;
     op->tiles_w = ceil_div(p.W, kTileW);
     op->tiles_h = ceil_div(p.H, kTileH);
     op->ntiles = op->tiles_w * op->tiles_h * p.B;
-    const int nsuper = ceil_div(op->ntiles, cs);
-    int nclusters = device_info().num_sms / cs;
-    if (nclusters > nsuper) nclusters = nsuper;
-    op->grid = nclusters * cs;
+    op->grid = op->ntiles < device_info().num_sms ? op->ntiles : device_info().num_sms;
     return SINDDM_OK;
 }
 
 int tc_conv_launch(const TcConvOp& op, cudaStream_t stream) {
     static int smem_set = 0;
-    if (smem_set < op.smem_bytes) {
+    if (!smem_set) {
         SINDDM_CUDA_OK(cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             device_info().max_smem_optin));
-        smem_set = device_info().max_smem_optin;
+        smem_set = 1;
     }
     const ConvProblem& p = op.p;
     KernelArgs a;
@@ -414,27 +402,12 @@ int tc_conv_launch(const TcConvOp& op, cudaStream_t stream) {
     a.ntiles = op.ntiles;
     a.nstages = op.nstages;
     a.stage_bytes = op.stage_bytes;
-    a.idesc = umma_idesc_tf32(kBM, p.N, 0, 0);
+    a.slot_stride = (int)align_up((size_t)p.N, 32);
+    a.idesc = umma_idesc_tf32(128, p.N, 0, 0);
     a.ep = p.ep;
     // algorithmic work: real pixels x N x (taps*Cin + Cres) MACs
     prof_begin(stream, 0, 2.0 * (double)p.B * p.H * p.W * p.N * ((double)p.ntaps * p.Cin + a.Cres));
-    a.cs = op.cs;
-    a.b_rows = p.N / op.cs;
-    a.nsuper = ceil_div(op.ntiles, op.cs);
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(op.grid);
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = op.smem_bytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = op.cs;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    SINDDM_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_conv_kernel, op.tm_a, op.tm_ares, op.tm_b, op.tm_bres, a));
+    tc_conv_kernel<<<op.grid, kThreads, op.smem_bytes, stream>>>(op.tm_a, op.tm_ares, op.tm_b, op.tm_bres, a);
     prof_end(stream);
     SINDDM_CUDA_OK(cudaGetLastError());
     return SINDDM_OK;
