@@ -15,7 +15,8 @@ namespace sinddm {
 
 namespace {
 
-constexpr int kSeg = 64;  // pixels per row segment
+constexpr int kSeg = 64;          // pixels per row segment
+constexpr int kRowsPerBlock = 8;  // image rows per CTA (threadIdx.y)
 
 constexpr int kRing = 8;  // window ring: 5 live columns + 3 columns of load-ahead (hides L2 latency)
 
@@ -71,16 +72,14 @@ __global__ void __launch_bounds__(256)
 dw5x5_kernel(const float* __restrict__ in, const float* __restrict__ wgt, const float* __restrict__ bias,
              const float* __restrict__ cond, const float* __restrict__ add, float* __restrict__ out, int B, int H,
              int W, int C, int flip, int round) {
+    // block = 32 channels x 8 image rows of one 64-px segment: the 8 row-warps read overlapping input rows
+    // at the same time, so 12 input rows are fetched from L2 per 8 output rows (L1 serves the rest)
     const int nseg = (W + kSeg - 1) / kSeg;
-    const long long total = (long long)B * H * nseg * C;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int c = (int)(idx % C);
-    long long r = idx / C;
-    const int seg = (int)(r % nseg);
-    r /= nseg;
-    const int h = (int)(r % H);
-    const int b = (int)(r / H);
+    const int seg = blockIdx.x % nseg;
+    const int c = (blockIdx.x / nseg) * 32 + threadIdx.x;
+    const int h = blockIdx.y * kRowsPerBlock + threadIdx.y;
+    const int b = blockIdx.z;
+    if (c >= C || h >= H) return;
 
     float wr[5][5];
 #pragma unroll
@@ -113,31 +112,25 @@ dw5x5_kernel(const float* __restrict__ in, const float* __restrict__ wgt, const 
 // ---------------------------------------------------------------------------------------------------
 constexpr int kRowsPerChunk = 8;
 
-__global__ void __launch_bounds__(512)
-dw5x5_wgrad_partial_kernel(const float* __restrict__ x, const float* __restrict__ dh,
-                                           float* __restrict__ scratch, int B, int H, int W, int C, int nchunk) {
-    extern __shared__ float red[];  // [lanes][26][C]
-    const int c = threadIdx.x;
-    const int ly = threadIdx.y;
-    const int lanes = blockDim.y;
-    const int chunk = blockIdx.x % nchunk;
-    const int b = blockIdx.x / nchunk;
-    const int h_begin = chunk * kRowsPerChunk;
-    const int h_end = min(H, h_begin + kRowsPerChunk);
-    const int nseg = (W + kSeg - 1) / kSeg;
-    const int nunits = (h_end - h_begin) * nseg;
+__global__ void __launch_bounds__(256)
+dw5x5_wgrad_partial_kernel(const float* __restrict__ x, const float* __restrict__ dh, float* __restrict__ scratch,
+                           int B, int H, int W, int C, int nchunk) {
+    __shared__ float red[kRowsPerChunk][26][32];
+    const int lane = threadIdx.x;           // channel within the 32-channel group
+    const int ry = threadIdx.y;             // image row within the chunk
+    const int c = blockIdx.x * 32 + lane;
+    const int chunk = blockIdx.y;
+    const int b = blockIdx.z;
+    const int h = chunk * kRowsPerChunk + ry;
 
     float acc[5][5];
 #pragma unroll
     for (int t = 0; t < 25; ++t) acc[t / 5][t % 5] = 0.f;
     float gsum = 0.f;
 
-    for (int u = ly; u < nunits; u += lanes) {
-        const int h = h_begin + u / nseg;
-        const int w0 = (u % nseg) * kSeg;
-        const int w1 = min(W, w0 + kSeg);
+    if (c < C && h < H) {
         const float* dhrow = dh + (((size_t)b * H + h) * W) * C + c;
-        slide_row(x, b, h, w0, w1, c, H, W, C, [&](int wo, const float (&xv)[5][5]) {
+        slide_row(x, b, h, 0, W, c, H, W, C, [&](int wo, const float (&xv)[5][5]) {
             const float g = __ldg(dhrow + (size_t)wo * C);
             gsum += g;
 #pragma unroll
@@ -147,14 +140,18 @@ dw5x5_wgrad_partial_kernel(const float* __restrict__ x, const float* __restrict_
         });
     }
 #pragma unroll
-    for (int t = 0; t < 25; ++t) red[(ly * 26 + t) * C + c] = acc[t / 5][t % 5];
-    red[(ly * 26 + 25) * C + c] = gsum;
+    for (int t = 0; t < 25; ++t) red[ry][t][lane] = acc[t / 5][t % 5];
+    red[ry][25][lane] = gsum;
     __syncthreads();
-    if (ly == 0) {
-        for (int i = 0; i < 26; ++i) {
+    // 256 threads reduce 26 x 32 sums over the 8 rows
+    for (int i = threadIdx.y * 32 + lane; i < 26 * 32; i += 256) {
+        const int t = i / 32, l = i % 32;
+        const int cc = blockIdx.x * 32 + l;
+        if (cc < C) {
             float s = 0.f;
-            for (int y = 0; y < lanes; ++y) s += red[(y * 26 + i) * C + c];
-            scratch[(((size_t)b * nchunk + chunk) * 26 + i) * C + c] = s;
+#pragma unroll
+            for (int y = 0; y < kRowsPerChunk; ++y) s += red[y][t][l];
+            scratch[(((size_t)b * nchunk + chunk) * 26 + t) * C + cc] = s;
         }
     }
 }
@@ -183,11 +180,11 @@ __global__ void dw5x5_wgrad_final_kernel(const float* __restrict__ scratch, floa
 
 int dw5x5_launch(const float* in, const float* w, const float* bias, const float* cond, const float* add, float* out,
                  int B, int H, int W, int C, int flip, int round_tf32, cudaStream_t stream) {
+    SINDDM_REQUIRE(B <= 65535, "dw5x5: batch too large");
     const int nseg = ceil_div(W, kSeg);
-    const long long total = (long long)B * H * nseg * C;
-    const long long blocks = (total + 255) / 256;
-    SINDDM_REQUIRE(blocks < (1ll << 31), "dw5x5: problem too large");
-    dw5x5_kernel<<<(unsigned)blocks, 256, 0, stream>>>(in, w, bias, cond, add, out, B, H, W, C, flip, round_tf32);
+    dim3 grid(nseg * ceil_div(C, 32), ceil_div(H, kRowsPerBlock), B);
+    dim3 block(32, kRowsPerBlock);
+    dw5x5_kernel<<<grid, block, 0, stream>>>(in, w, bias, cond, add, out, B, H, W, C, flip, round_tf32);
     SINDDM_CUDA_OK(cudaGetLastError());
     return SINDDM_OK;
 }
@@ -198,20 +195,11 @@ size_t dw5x5_wgrad_scratch_floats(int B, int H, int C) {
 
 int dw5x5_wgrad_launch(const float* x, const float* dh, float* dw, float* db, float* dcond, float* scratch, int B,
                        int H, int W, int C, cudaStream_t stream) {
-    SINDDM_REQUIRE(C <= 256, "dw5x5_wgrad: C=%d too large", C);
+    SINDDM_REQUIRE(B <= 65535, "dw5x5_wgrad: batch too large");
     const int nchunk = ceil_div(H, kRowsPerChunk);
-    int lanes = 512 / C;
-    if (lanes < 1) lanes = 1;
-    if (lanes > 16) lanes = 16;
-    dim3 block(C, lanes);
-    const size_t smem = (size_t)lanes * 26 * C * sizeof(float);
-    static int attr_set = 0;
-    if (smem > 48 * 1024 && !attr_set) {
-        SINDDM_CUDA_OK(cudaFuncSetAttribute(dw5x5_wgrad_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            96 * 1024));
-        attr_set = 1;
-    }
-    dw5x5_wgrad_partial_kernel<<<B * nchunk, block, smem, stream>>>(x, dh, scratch, B, H, W, C, nchunk);
+    dim3 grid(ceil_div(C, 32), nchunk, B);
+    dim3 block(32, kRowsPerChunk);
+    dw5x5_wgrad_partial_kernel<<<grid, block, 0, stream>>>(x, dh, scratch, B, H, W, C, nchunk);
     SINDDM_CUDA_OK(cudaGetLastError());
     dim3 grid2(ceil_div(C, 64), 26);
     dw5x5_wgrad_final_kernel<<<grid2, 64, 0, stream>>>(scratch, dw, db, dcond, B, C, nchunk);
