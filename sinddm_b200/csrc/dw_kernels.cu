@@ -176,11 +176,190 @@ __global__ void dw5x5_wgrad_final_kernel(const float* __restrict__ scratch, floa
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// TMA-staged versions (C % 4 == 0): the (8+4) x (32+4) pixel x 32 channel halo tile is brought into shared
+// memory by ONE bulk-tensor copy whose out-of-image part TMA zero-fills (= the conv's zero padding, no
+// bounds code at all); thread (channel, row) then slides its 5x5 window along the 32 columns reading
+// 5 shared-memory words per output (a warp = 32 channels of one pixel = one conflict-free 128-byte row).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kTW = 32;                                  // output columns per tile
+constexpr int kTH = 8;                                   // output rows per tile (= threadIdx.y)
+constexpr int kTileCols = kTW + 4, kTileRows = kTH + 4;
+constexpr int kTileFloats = kTileRows * kTileCols * 32;  // 13824 floats = 55296 B
+
+template <typename Body>
+SINDDM_DEVINL void slide_smem(const float* tile, int ry, int lane, Body&& body) {
+    // win[ky][slot], slot = tile column modulo 5
+    float win[5][5];
+    const float* base = tile + (size_t)ry * kTileCols * 32 + lane;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int ky = 0; ky < 5; ++ky) win[ky][j] = base[(ky * kTileCols + j) * 32];
+    for (int w = 0; w < kTW; w += 5) {
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const int wo = w + j;
+            if (wo < kTW) {
+#pragma unroll
+                for (int ky = 0; ky < 5; ++ky) win[ky][(j + 4) % 5] = base[(ky * kTileCols + wo + 4) * 32];
+                float x[5][5];
+#pragma unroll
+                for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 5; ++kx) x[ky][kx] = win[ky][(j + kx) % 5];
+                body(wo, x);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+dw5x5_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ wgt,
+                 const float* __restrict__ bias, const float* __restrict__ cond, const float* __restrict__ add,
+                 float* __restrict__ out, int H, int W, int C, int tiles_w, int flip, int round) {
+    extern __shared__ __align__(128) uint8_t dsm[];
+    float* tile = reinterpret_cast<float*>(dsm);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(dsm + kTileFloats * sizeof(float));
+    const int lane = threadIdx.x, ry = threadIdx.y;
+    const int tw = blockIdx.x % tiles_w;
+    const int cg = blockIdx.x / tiles_w;
+    const int th = blockIdx.y, b = blockIdx.z;
+    const int tid = ry * 32 + lane;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_arrive_expect_tx(bar, kTileFloats * sizeof(float));
+        tma_load_4d(tile, &tm_in, bar, cg * 32, tw * kTW - 2, th * kTH - 2, b);
+    }
+    const int c = cg * 32 + lane;
+    const int h = th * kTH + ry;
+    const bool cok = c < C;
+    float wr[5][5];
+#pragma unroll
+    for (int t = 0; t < 25; ++t) wr[t / 5][t % 5] = cok ? __ldg(wgt + c * 25 + (flip ? 24 - t : t)) : 0.f;
+    const float bv = (bias && cok) ? __ldg(bias + c) : 0.f;
+    const float cv = (cond && cok) ? __ldg(cond + (size_t)b * C + c) : 0.f;
+    mbar_wait(bar, 0);
+    if (!cok || h >= H) return;
+    const size_t rowoff = (((size_t)b * H + h) * W) * C + c;
+    const int w0 = tw * kTW;
+    slide_smem(tile, ry, lane, [&](int wo, const float (&x)[5][5]) {
+        const int w = w0 + wo;
+        if (w < W) {
+            float acc = 0.f;
+#pragma unroll
+            for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 5; ++kx) acc = fmaf(x[ky][kx], wr[ky][kx], acc);
+            const size_t off = rowoff + (size_t)w * C;
+            float v = (acc + bv) + cv;           // reference order: (conv + bias) + condition
+            if (add) v += __ldg(add + off);
+            if (round) v = round_tf32(v);
+            out[off] = v;
+        }
+    });
+}
+
+// grid = (channel groups, row chunks, B); the CTA walks the column tiles of its 8-row chunk with a
+// double-buffered TMA pipeline and keeps the 26 sums per (channel, row) in registers.
+__global__ void __launch_bounds__(256)
+dw5x5_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __restrict__ dh,
+                       float* __restrict__ scratch, int H, int W, int C, int tiles_w, int nchunk) {
+    extern __shared__ __align__(128) uint8_t dsm[];
+    float* tiles = reinterpret_cast<float*>(dsm);   // 2 buffers; reused for the final reduction
+    uint64_t* bar = reinterpret_cast<uint64_t*>(dsm + 2 * kTileFloats * sizeof(float));
+    const int lane = threadIdx.x, ry = threadIdx.y;
+    const int cg = blockIdx.x, chunk = blockIdx.y, b = blockIdx.z;
+    const int tid = ry * 32 + lane;
+    const int c = cg * 32 + lane;
+    const int h = chunk * kTH + ry;
+    const bool active = c < C && h < H;
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_arrive_expect_tx(&bar[0], kTileFloats * sizeof(float));
+        tma_load_4d(tiles, &tm_x, &bar[0], cg * 32, -2, chunk * kTH - 2, b);
+    }
+    float acc[5][5];
+#pragma unroll
+    for (int t = 0; t < 25; ++t) acc[t / 5][t % 5] = 0.f;
+    float gsum = 0.f;
+    const float* dhrow = dh + (((size_t)b * H + (h < H ? h : 0)) * W) * C + (c < C ? c : 0);
+
+    for (int tw = 0; tw < tiles_w; ++tw) {
+        const int buf = tw & 1;
+        if (tid == 0 && tw + 1 < tiles_w) {
+            // the other buffer was consumed in iteration tw-1 (all threads passed the __syncthreads below)
+            mbar_arrive_expect_tx(&bar[buf ^ 1], kTileFloats * sizeof(float));
+            tma_load_4d(tiles + (size_t)(buf ^ 1) * kTileFloats, &tm_x, &bar[buf ^ 1], cg * 32, (tw + 1) * kTW - 2,
+                        chunk * kTH - 2, b);
+        }
+        mbar_wait(&bar[buf], (uint32_t)(tw >> 1) & 1u);
+        if (active) {
+            const int w0 = tw * kTW;
+            slide_smem(tiles + (size_t)buf * kTileFloats, ry, lane, [&](int wo, const float (&xv)[5][5]) {
+                const int w = w0 + wo;
+                if (w < W) {
+                    const float g = __ldg(dhrow + (size_t)w * C);
+                    gsum += g;
+#pragma unroll
+                    for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+                        for (int kx = 0; kx < 5; ++kx) acc[ky][kx] = fmaf(xv[ky][kx], g, acc[ky][kx]);
+                }
+            });
+        }
+        __syncthreads();   // everyone is done with `buf` before it is refilled two iterations later
+    }
+    // reduce over the 8 rows through shared memory (the tile buffers are free now)
+    float* red = tiles;    // [8][26][32]
+#pragma unroll
+    for (int t = 0; t < 25; ++t) red[(ry * 26 + t) * 32 + lane] = active ? acc[t / 5][t % 5] : 0.f;
+    red[(ry * 26 + 25) * 32 + lane] = active ? gsum : 0.f;
+    __syncthreads();
+    for (int i = tid; i < 26 * 32; i += 256) {
+        const int t = i / 32, l = i % 32;
+        const int cc = cg * 32 + l;
+        if (cc < C) {
+            float s = 0.f;
+#pragma unroll
+            for (int y = 0; y < kTH; ++y) s += red[(y * 26 + t) * 32 + l];
+            scratch[(((size_t)b * nchunk + chunk) * 26 + t) * C + cc] = s;
+        }
+    }
+}
+
 }  // namespace
 
 int dw5x5_launch(const float* in, const float* w, const float* bias, const float* cond, const float* add, float* out,
                  int B, int H, int W, int C, int flip, int round_tf32, cudaStream_t stream) {
     SINDDM_REQUIRE(B <= 65535, "dw5x5: batch too large");
+    if (C % 4 == 0 && device_info().initialized) {
+        CUtensorMap tm;
+        SINDDM_TRY(make_tmap_nhwc(&tm, in, B, H, W, C, 32, kTileCols, kTileRows, CU_TENSOR_MAP_SWIZZLE_NONE));
+        const int tiles_w = ceil_div(W, kTW);
+        const size_t smem = kTileFloats * sizeof(float) + 16;
+        static int attr_set = 0;
+        if (!attr_set) {
+            SINDDM_CUDA_OK(cudaFuncSetAttribute(dw5x5_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)smem));
+            attr_set = 1;
+        }
+        dim3 grid(tiles_w * ceil_div(C, 32), ceil_div(H, kTH), B);
+        dim3 block(32, kTH);
+        dw5x5_tma_kernel<<<grid, block, smem, stream>>>(tm, w, bias, cond, add, out, H, W, C, tiles_w, flip,
+                                                        round_tf32);
+        SINDDM_CUDA_OK(cudaGetLastError());
+        return SINDDM_OK;
+    }
     const int nseg = ceil_div(W, kSeg);
     dim3 grid(nseg * ceil_div(C, 32), ceil_div(H, kRowsPerBlock), B);
     dim3 block(32, kRowsPerBlock);
@@ -196,10 +375,24 @@ size_t dw5x5_wgrad_scratch_floats(int B, int H, int C) {
 int dw5x5_wgrad_launch(const float* x, const float* dh, float* dw, float* db, float* dcond, float* scratch, int B,
                        int H, int W, int C, cudaStream_t stream) {
     SINDDM_REQUIRE(B <= 65535, "dw5x5_wgrad: batch too large");
+    static_assert(kRowsPerChunk == kTH, "scratch layout assumes 8-row chunks in both kernels");
     const int nchunk = ceil_div(H, kRowsPerChunk);
     dim3 grid(ceil_div(C, 32), nchunk, B);
     dim3 block(32, kRowsPerChunk);
-    dw5x5_wgrad_partial_kernel<<<grid, block, 0, stream>>>(x, dh, scratch, B, H, W, C, nchunk);
+    if (C % 4 == 0 && device_info().initialized) {
+        CUtensorMap tm;
+        SINDDM_TRY(make_tmap_nhwc(&tm, x, B, H, W, C, 32, kTileCols, kTileRows, CU_TENSOR_MAP_SWIZZLE_NONE));
+        const size_t smem = 2 * kTileFloats * sizeof(float) + 16;
+        static int attr_set = 0;
+        if (!attr_set) {
+            SINDDM_CUDA_OK(cudaFuncSetAttribute(dw5x5_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)smem));
+            attr_set = 1;
+        }
+        dw5x5_wgrad_tma_kernel<<<grid, block, smem, stream>>>(tm, dh, scratch, H, W, C, ceil_div(W, kTW), nchunk);
+    } else {
+        dw5x5_wgrad_partial_kernel<<<grid, block, 0, stream>>>(x, dh, scratch, B, H, W, C, nchunk);
+    }
     SINDDM_CUDA_OK(cudaGetLastError());
     dim3 grid2(ceil_div(C, 64), 26);
     dw5x5_wgrad_final_kernel<<<grid2, 64, 0, stream>>>(scratch, dw, db, dcond, B, C, nchunk);
