@@ -43,6 +43,24 @@ SINDDM_DEVINL uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// True in exactly one lane of a fully converged warp.  tcgen05.mma / TMA / tcgen05.commit are issued through
+// the uniform datapath: they must sit in WARP-UNIFORM control flow guarded by this predicate.  Guarding them
+// with `lane == 0` instead makes the compiler wrap each one in an ELECT/branch loop over the active lanes,
+// which costs ~200 cycles per instruction (measured with tools/mma_bench.cu).
+SINDDM_DEVINL bool elect_one_sync() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 rx;\n\t"
+        ".reg .pred px;\n\t"
+        "elect.sync rx|px, %1;\n\t"
+        "@px mov.s32 %0, 1;\n\t"
+        "}\n"
+        : "+r"(pred)
+        : "r"(0xffffffffu));
+    return pred != 0;
+}
+
 SINDDM_DEVINL float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -118,6 +136,35 @@ SINDDM_DEVINL void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t*
         : "memory");
 }
 
+// Whole-warp ("_w") versions: executed by all 32 lanes of a converged warp, the lane election happens inside
+// the asm by predication, so the surrounding loop stays in uniform control flow (see elect_one_sync()).
+SINDDM_DEVINL void mbar_arrive_expect_tx_w(uint64_t* bar, uint32_t bytes) {
+    asm volatile(
+        "{\n\t.reg .pred pe;\n\t.reg .b32 rx;\n\telect.sync rx|pe, 0xffffffff;\n\t"
+        "@pe mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}\n" ::"r"(smem_u32(bar)),
+        "r"(bytes)
+        : "memory");
+}
+
+SINDDM_DEVINL void tma_load_2d_w(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "{\n\t.reg .pred pe;\n\t.reg .b32 rx;\n\telect.sync rx|pe, 0xffffffff;\n\t"
+        "@pe cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+        "[%2];\n\t}\n" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+SINDDM_DEVINL void tma_load_4d_w(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                 int c3) {
+    asm volatile(
+        "{\n\t.reg .pred pe;\n\t.reg .b32 rx;\n\telect.sync rx|pe, 0xffffffff;\n\t"
+        "@pe cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+        "%6}], [%2];\n\t}\n" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
 // Multicast variant: the box is written at the same CTA-relative smem offset of every CTA in `cta_mask`
 // and completes bytes on the mbarrier at the same offset in each of them.
 SINDDM_DEVINL void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
@@ -175,6 +222,65 @@ SINDDM_DEVINL void umma_tf32_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
         "}\n" ::"r"(tmem_d),
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// Up to four back-to-back tf32 MMAs along K issued from ONE asm statement executed by the WHOLE (converged)
+// warp: the lane election and the per-K descriptor advance (+32 B = +2 in the >>4 encoded start address)
+// happen inside, with predication instead of branches.  Issue cost per MMA drops from ~250 cycles (C++ loop
+// with `if (elect)` around a single-MMA asm: convergence-barrier + R2UR chain per instruction, measured with
+// tools/mma_bench.cu) to a few tens of cycles.
+//   a_lo / b_lo : low 32 bits of the smem descriptors of the first K slice;  hi: shared high 32 bits
+//   step_lo     : descriptor advance per K slice (2 for K-major 128B-swizzle rows, 64 for MN-major boxes)
+//   nk          : number of K slices to issue (1..4);  acc_first: accumulate flag of the first one
+SINDDM_DEVINL void umma_tf32_ss_x4(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t step_lo,
+                                   uint32_t idesc, uint32_t acc_first, uint32_t nk) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pe, pacc, pone, p1, p2, p3;\n\t"
+        ".reg .b32 rx, a1, a2, a3, b1, b2, b3;\n\t"
+        ".reg .b64 da0, da1, da2, da3, db0, db1, db2, db3;\n\t"
+        "elect.sync rx|pe, 0xffffffff;\n\t"
+        "setp.ne.b32 pacc, %6, 0;\n\t"
+        "setp.eq.b32 pone, 0, 0;\n\t"
+        "setp.gt.u32 p1, %7, 1;\n\t"
+        "setp.gt.u32 p2, %7, 2;\n\t"
+        "setp.gt.u32 p3, %7, 3;\n\t"
+        "and.pred p1, p1, pe;\n\t"
+        "and.pred p2, p2, pe;\n\t"
+        "and.pred p3, p3, pe;\n\t"
+        "add.u32 a1, %1, %4;\n\t"
+        "add.u32 a2, a1, %4;\n\t"
+        "add.u32 a3, a2, %4;\n\t"
+        "add.u32 b1, %2, %4;\n\t"
+        "add.u32 b2, b1, %4;\n\t"
+        "add.u32 b3, b2, %4;\n\t"
+        "mov.b64 da0, {%1, %3};\n\t"
+        "mov.b64 da1, {a1, %3};\n\t"
+        "mov.b64 da2, {a2, %3};\n\t"
+        "mov.b64 da3, {a3, %3};\n\t"
+        "mov.b64 db0, {%2, %3};\n\t"
+        "mov.b64 db1, {b1, %3};\n\t"
+        "mov.b64 db2, {b2, %3};\n\t"
+        "mov.b64 db3, {b3, %3};\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], da0, db0, %5, pacc;\n\t"
+        "@p1 tcgen05.mma.cta_group::1.kind::tf32 [%0], da1, db1, %5, pone;\n\t"
+        "@p2 tcgen05.mma.cta_group::1.kind::tf32 [%0], da2, db2, %5, pone;\n\t"
+        "@p3 tcgen05.mma.cta_group::1.kind::tf32 [%0], da3, db3, %5, pone;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(hi), "r"(step_lo), "r"(idesc), "r"(acc_first), "r"(nk)
+        : "memory");
+}
+
+// Whole-warp version of umma_commit: one elected lane arrives.
+SINDDM_DEVINL void umma_commit_elect(uint64_t* bar) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pe;\n\t"
+        ".reg .b32 rx;\n\t"
+        "elect.sync rx|pe, 0xffffffff;\n\t"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+        "}\n" ::"r"(smem_u32(bar))
         : "memory");
 }
 

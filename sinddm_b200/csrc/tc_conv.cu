@@ -81,7 +81,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     float* s_wfinal = s_wres3 + kMaxN * 3;
     float* s_bfinal = s_wfinal + 3 * kMaxN;
 
-    const int warp = threadIdx.x >> 5;
+    // warp index through a shuffle so the compiler can prove the role branches are warp-uniform
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
     const int N = a.N;
 
@@ -125,94 +126,90 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     const int nst = nst_main + a.nchunks_res;        // stages per tile
     const uint32_t nbytes = (uint32_t)N * kKC * 4;   // one weight box
 
+    // Roles 0 and 1 run their loops with ALL 32 lanes (uniform control flow); TMA, MMA and commit instructions
+    // elect their single issuing lane inside the asm (common.cuh) -- see elect_one_sync() for why.
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-                const int tw = tile % a.tiles_w;
-                const int th = (tile / a.tiles_w) % a.tiles_h;
-                const int b = tile / (a.tiles_w * a.tiles_h);
-                const int h0 = th * kTileH, w0 = tw * kTileW;
-                for (int it = 0; it < nst; ++it) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1u);
-                    uint8_t* sa = smem + (size_t)stage * a.stage_bytes;
-                    uint8_t* sb = sa + kABytes;
-                    if (it < nst_main) {
-                        const int c = it / nkx;
-                        const int kx = it - c * nkx;
-                        mbar_arrive_expect_tx(&full_bar[stage], kABytes + (uint32_t)nky * nbytes);
-                        // rows h0-1 .. h0+16, columns shifted by the horizontal tap (centre column for 1x1)
-                        tma_load_4d(sa, &tm_a, &full_bar[stage], c * kKC, w0 + (nkx == 3 ? kx - 1 : 0), h0 - 1, b);
-                        for (int ky = 0; ky < nky; ++ky) {
-                            const int tap = nkx == 3 ? ky * 3 + kx : 0;
-                            tma_load_2d(sb + (size_t)ky * nbytes, &tm_b, &full_bar[stage], c * kKC, tap * N);
-                        }
-                    } else {
-                        const int c = it - nst_main;
-                        mbar_arrive_expect_tx(&full_bar[stage], kABytes + nbytes);
-                        tma_load_4d(sa, &tm_ares, &full_bar[stage], c * kKC, w0, h0 - 1, b);
-                        tma_load_2d(sb, &tm_bres, &full_bar[stage], c * kKC, 0);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+            const int tw = tile % a.tiles_w;
+            const int th = (tile / a.tiles_w) % a.tiles_h;
+            const int b = tile / (a.tiles_w * a.tiles_h);
+            const int h0 = th * kTileH, w0 = tw * kTileW;
+            for (int it = 0; it < nst; ++it) {
+                mbar_wait(&empty_bar[stage], phase ^ 1u);
+                uint8_t* sa = smem + (size_t)stage * a.stage_bytes;
+                uint8_t* sb = sa + kABytes;
+                if (it < nst_main) {
+                    const int c = it / nkx;
+                    const int kx = it - c * nkx;
+                    mbar_arrive_expect_tx_w(&full_bar[stage], kABytes + (uint32_t)nky * nbytes);
+                    // rows h0-1 .. h0+16, columns shifted by the horizontal tap (centre column for 1x1)
+                    tma_load_4d_w(sa, &tm_a, &full_bar[stage], c * kKC, w0 + (nkx == 3 ? kx - 1 : 0), h0 - 1, b);
+                    for (int ky = 0; ky < nky; ++ky) {
+                        const int tap = nkx == 3 ? ky * 3 + kx : 0;
+                        tma_load_2d_w(sb + (size_t)ky * nbytes, &tm_b, &full_bar[stage], c * kKC, tap * N);
                     }
-                    if (++stage == a.nstages) {
-                        stage = 0;
-                        phase ^= 1u;
-                    }
+                } else {
+                    const int c = it - nst_main;
+                    mbar_arrive_expect_tx_w(&full_bar[stage], kABytes + nbytes);
+                    tma_load_4d_w(sa, &tm_ares, &full_bar[stage], c * kKC, w0, h0 - 1, b);
+                    tma_load_2d_w(sb, &tm_bres, &full_bar[stage], c * kKC, 0);
+                }
+                if (++stage == a.nstages) {
+                    stage = 0;
+                    phase ^= 1u;
                 }
             }
         }
-        __syncwarp();
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            uint32_t slot_uses[kSlots] = {0, 0, 0};
-            int titer = 0;
-            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++titer) {
-                const int s0 = (2 * titer) % kSlots, s1 = (2 * titer + 1) % kSlots;
-                // the slot must have been drained by the epilogue of its previous use
-                mbar_wait(&tempty_bar[s0], (slot_uses[s0] & 1u) ^ 1u);
-                mbar_wait(&tempty_bar[s1], (slot_uses[s1] & 1u) ^ 1u);
-                ++slot_uses[s0];
-                ++slot_uses[s1];
+        int stage = 0;
+        uint32_t phase = 0;
+        uint32_t slot_uses[kSlots] = {0, 0, 0};
+        int titer = 0;
+        // high 32 bits of every operand descriptor: SBO = 1024 B, version 1, 128B swizzle
+        const uint32_t desc_hi = (uint32_t)(umma_smem_desc(0, 0, 1024, UMMA_LAYOUT_SW128) >> 32);
+        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++titer) {
+            const int s0 = (2 * titer) % kSlots, s1 = (2 * titer + 1) % kSlots;
+            // the slot must have been drained by the epilogue of its previous use
+            mbar_wait(&tempty_bar[s0], (slot_uses[s0] & 1u) ^ 1u);
+            mbar_wait(&tempty_bar[s1], (slot_uses[s1] & 1u) ^ 1u);
+            ++slot_uses[s0];
+            ++slot_uses[s1];
+            tc_fence_after_sync();
+            const uint32_t d0 = tmem_base + (uint32_t)(s0 * a.slot_stride);
+            const uint32_t d1 = tmem_base + (uint32_t)(s1 * a.slot_stride);
+            for (int it = 0; it < nst; ++it) {
+                mbar_wait(&full_bar[stage], phase);
                 tc_fence_after_sync();
-                const uint32_t d0 = tmem_base + (uint32_t)(s0 * a.slot_stride);
-                const uint32_t d1 = tmem_base + (uint32_t)(s1 * a.slot_stride);
-                for (int it = 0; it < nst; ++it) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after_sync();
-                    const uint32_t sa = smem_u32(smem + (size_t)stage * a.stage_bytes);
-                    const uint32_t sb = sa + kABytes;
-                    const bool main = it < nst_main;
-                    const int cvalid = main ? min(kKC, a.Cin - (it / nkx) * kKC) : min(kKC, a.Cres - (it - nst_main) * kKC);
-                    const int nmma = cvalid >> 3;  // K = 8 tf32 per instruction
-                    const int kys = main ? nky : 1;
-                    for (int ky = 0; ky < kys; ++ky) {
-                        // vertical tap = row offset into the halo box; the 1x1 / residual case reads the centre rows
-                        const int row0 = (main && nky == 3) ? ky : 1;
-                        const uint32_t a0 = sa + (uint32_t)row0 * kRowBytes;
-                        const uint32_t a1 = a0 + 8u * kRowBytes;
-                        const uint32_t bb = sb + (uint32_t)ky * nbytes;
-                        for (int k = 0; k < nmma; ++k) {
-                            const uint32_t acc = (it | ky | k) != 0 ? 1u : 0u;
-                            const uint64_t db = umma_smem_desc(bb + k * 32, 0, 1024, UMMA_LAYOUT_SW128);
-                            umma_tf32_ss(d0, umma_smem_desc(a0 + k * 32, 0, 1024, UMMA_LAYOUT_SW128), db, a.idesc, acc);
-                            umma_tf32_ss(d1, umma_smem_desc(a1 + k * 32, 0, 1024, UMMA_LAYOUT_SW128), db, a.idesc, acc);
-                        }
-                    }
-                    umma_commit(&empty_bar[stage]);
-                    if (++stage == a.nstages) {
-                        stage = 0;
-                        phase ^= 1u;
-                    }
+                const uint32_t sa = smem_u32(smem + (size_t)stage * a.stage_bytes);
+                const uint32_t sb = sa + kABytes;
+                const bool main = it < nst_main;
+                const int cvalid = main ? min(kKC, a.Cin - (it / nkx) * kKC) : min(kKC, a.Cres - (it - nst_main) * kKC);
+                const uint32_t nmma = (uint32_t)(cvalid >> 3);  // K = 8 tf32 per instruction, <= 4 per chunk
+                const int kys = main ? nky : 1;
+                for (int ky = 0; ky < kys; ++ky) {
+                    // vertical tap = row offset into the halo box; the 1x1 / residual case reads the centre rows
+                    const int row0 = (main && nky == 3) ? ky : 1;
+                    const uint32_t a0 = ((sa + (uint32_t)row0 * kRowBytes) >> 4) & 0x3FFFu;
+                    const uint32_t a1 = ((sa + (uint32_t)(row0 + 8) * kRowBytes) >> 4) & 0x3FFFu;
+                    const uint32_t bb = ((sb + (uint32_t)ky * nbytes) >> 4) & 0x3FFFu;
+                    const uint32_t acc = (it | ky) != 0 ? 1u : 0u;
+                    // K slices advance by 32 B inside the 128B-swizzled rows: +2 in the encoded start address
+                    umma_tf32_ss_x4(d0, a0, bb, desc_hi, 2u, a.idesc, acc, nmma);
+                    umma_tf32_ss_x4(d1, a1, bb, desc_hi, 2u, a.idesc, acc, nmma);
                 }
-                umma_commit(&tfull_bar[s0]);
-                umma_commit(&tfull_bar[s1]);
+                umma_commit_elect(&empty_bar[stage]);
+                if (++stage == a.nstages) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
             }
+            umma_commit_elect(&tfull_bar[s0]);
+            umma_commit_elect(&tfull_bar[s1]);
         }
-        __syncwarp();
     } else {
         // ------------------------------------------------------------ epilogue warps
         const int quarter = warp & 3;             // TMEM lane quarter this warp may read

@@ -52,7 +52,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     uint64_t* done_bar = empty_bar + 8;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
     const int lane = threadIdx.x & 31;
     const int group = blockIdx.y;
     const int split = blockIdx.x;
@@ -86,72 +86,66 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
 
     const int a_bytes = nslots * kBoxBytes;  // x region of a stage; dy region follows
 
+    // Roles 0 and 1 run with all 32 lanes in uniform control flow; the issuing lane is elected inside the asm.
     if (warp == 0) {
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            const uint32_t tx_bytes = (uint32_t)(nvalid + a.cyk) * kBoxBytes;
-            for (int ks = ks_begin; ks < ks_end; ++ks) {
-                const int per_img = a.H * a.wt;
-                const int b = ks / per_img;
-                const int r = ks - b * per_img;
-                const int h = r / a.wt;
-                const int w0 = (r - h * a.wt) * kKP;
-                mbar_wait(&empty_bar[stage], phase ^ 1u);
-                uint8_t* sx = smem + (size_t)stage * a.stage_bytes;
-                uint8_t* sy = sx + a_bytes;
-                mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-                for (int j = 0; j < a.cyk; ++j)
-                    tma_load_4d(sy + j * kBoxBytes, &tm_dy, &full_bar[stage], j * kCC, w0, h, b);
-                for (int q = 0; q < nvalid; ++q) {
-                    const int gq = g0 + q;
-                    const int tap = gq / a.cxk;
-                    const int j = gq - tap * a.cxk;
-                    int dy = 0, dx = 0;
-                    if (a.ntaps == 9) {
-                        dy = tap / 3 - 1;
-                        dx = tap % 3 - 1;
-                    }
-                    tma_load_4d(sx + q * kBoxBytes, &tm_x, &full_bar[stage], j * kCC, w0 + dx, h + dy, b);
+        int stage = 0;
+        uint32_t phase = 0;
+        const uint32_t tx_bytes = (uint32_t)(nvalid + a.cyk) * kBoxBytes;
+        for (int ks = ks_begin; ks < ks_end; ++ks) {
+            const int per_img = a.H * a.wt;
+            const int b = ks / per_img;
+            const int r = ks - b * per_img;
+            const int h = r / a.wt;
+            const int w0 = (r - h * a.wt) * kKP;
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            uint8_t* sx = smem + (size_t)stage * a.stage_bytes;
+            uint8_t* sy = sx + a_bytes;
+            mbar_arrive_expect_tx_w(&full_bar[stage], tx_bytes);
+            for (int j = 0; j < a.cyk; ++j)
+                tma_load_4d_w(sy + j * kBoxBytes, &tm_dy, &full_bar[stage], j * kCC, w0, h, b);
+            for (int q = 0; q < nvalid; ++q) {
+                const int gq = g0 + q;
+                const int tap = gq / a.cxk;
+                const int j = gq - tap * a.cxk;
+                int dy = 0, dx = 0;
+                if (a.ntaps == 9) {
+                    dy = tap / 3 - 1;
+                    dx = tap % 3 - 1;
                 }
-                if (++stage == a.nstages) {
-                    stage = 0;
-                    phase ^= 1u;
-                }
+                tma_load_4d_w(sx + q * kBoxBytes, &tm_x, &full_bar[stage], j * kCC, w0 + dx, h + dy, b);
+            }
+            if (++stage == a.nstages) {
+                stage = 0;
+                phase ^= 1u;
             }
         }
-        __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int ks = ks_begin; ks < ks_end; ++ks) {
-                mbar_wait(&full_bar[stage], phase);
-                tc_fence_after_sync();
-                const uint32_t sx = smem_u32(smem + (size_t)stage * a.stage_bytes);
-                const uint32_t sy = sx + a_bytes;
-                const uint32_t acc = (ks != ks_begin) ? 1u : 0u;
-                for (int i = 0; i < ntile_valid; ++i) {
-#pragma unroll
-                    for (int k8 = 0; k8 < kKP / 8; ++k8) {
-                        // MN-major, 128B swizzle with 32B atoms: 4-pixel atoms are 512 B apart (SBO),
-                        // 32-channel chunk boxes are kBoxBytes apart (LBO); 8 pixels per MMA = 1024 B.
-                        const uint64_t da = umma_smem_desc(sx + i * 4 * kBoxBytes + k8 * 1024, kBoxBytes, 512,
-                                                           UMMA_LAYOUT_SW128_B32);
-                        const uint64_t db = umma_smem_desc(sy + k8 * 1024, kBoxBytes, 512, UMMA_LAYOUT_SW128_B32);
-                        umma_tf32_ss(tmem_base + (uint32_t)(i * a.col_stride), da, db, a.idesc,
-                                     (acc | (uint32_t)k8) != 0 ? 1u : 0u);
-                    }
-                }
-                umma_commit(&empty_bar[stage]);
-                if (++stage == a.nstages) {
-                    stage = 0;
-                    phase ^= 1u;
-                }
+        int stage = 0;
+        uint32_t phase = 0;
+        // MN-major, 128B swizzle with 32B atoms: 4-pixel atoms are 512 B apart (SBO), 32-channel chunk boxes are
+        // kBoxBytes apart (LBO, bits 16.. of the low word); 8 pixels per MMA = 1024 B = +64 in the start address.
+        const uint64_t proto = umma_smem_desc(0, kBoxBytes, 512, UMMA_LAYOUT_SW128_B32);
+        const uint32_t desc_hi = (uint32_t)(proto >> 32);
+        const uint32_t lbo_lo = (uint32_t)proto;
+        for (int ks = ks_begin; ks < ks_end; ++ks) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after_sync();
+            const uint32_t sx = smem_u32(smem + (size_t)stage * a.stage_bytes);
+            const uint32_t sy = sx + a_bytes;
+            const uint32_t acc = (ks != ks_begin) ? 1u : 0u;
+            const uint32_t b_lo = lbo_lo | ((sy >> 4) & 0x3FFFu);
+            for (int i = 0; i < ntile_valid; ++i) {
+                const uint32_t a_lo = lbo_lo | (((sx + (uint32_t)i * 4u * kBoxBytes) >> 4) & 0x3FFFu);
+                umma_tf32_ss_x4(tmem_base + (uint32_t)(i * a.col_stride), a_lo, b_lo, desc_hi, 64u, a.idesc, acc,
+                                kKP / 8);
             }
-            umma_commit(done_bar);
+            umma_commit_elect(&empty_bar[stage]);
+            if (++stage == a.nstages) {
+                stage = 0;
+                phase ^= 1u;
+            }
         }
-        __syncwarp();
+        umma_commit_elect(done_bar);
     } else {
         // epilogue: one accumulator row (= one (tap, ci)) per thread, Cy contiguous floats each
         const int quarter = warp & 3;
