@@ -176,6 +176,16 @@ SINDDM_DEVINL void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, uint64
         : "memory");
 }
 
+SINDDM_DEVINL void tma_load_2d_mc_w(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                    uint16_t cta_mask) {
+    asm volatile(
+        "{\n\t.reg .pred pe;\n\t.reg .b32 rx;\n\telect.sync rx|pe, 0xffffffff;\n\t"
+        "@pe cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], "
+        "[%1, {%3, %4}], [%2], %5;\n\t}\n" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+        : "memory");
+}
+
 // ----------------------------------------------------------------------------------------------
 // thread-block clusters
 // ----------------------------------------------------------------------------------------------
@@ -297,6 +307,15 @@ SINDDM_DEVINL void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
     asm volatile(
         "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
             smem_u32(bar)),
+        "h"(cta_mask)
+        : "memory");
+}
+
+SINDDM_DEVINL void umma_commit_mc_elect(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile(
+        "{\n\t.reg .pred pe;\n\t.reg .b32 rx;\n\telect.sync rx|pe, 0xffffffff;\n\t"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}\n" ::
+            "r"(smem_u32(bar)),
         "h"(cta_mask)
         : "memory");
 }

@@ -17,6 +17,9 @@
 //         A(ky, half) = box + (ky + 8*half) * 16 px * 128 B
 //     so every loaded activation byte feeds 3 taps, and every weight byte (3 boxes [N][32] per stage) feeds
 //     256 pixels: 2.3x fewer bytes per FLOP than a tap-by-tap 128-pixel walk.
+//   * the halo boxes (36 KiB) and the weight boxes (N x 128 B, one per tap) travel through TWO independent
+//     mbarrier rings (3 activation slots, 5-8 weight slots), so ~200 KiB of loads stay in flight and the
+//     ~3000-cycle L2 latency is covered although one activation box feeds 24 MMAs.
 //   * operands land in 128B-swizzled K-major tiles that the UMMA descriptors consume directly.
 //   accumulators   fp32 in TMEM: three slots of N columns; tile pair p uses slots (2p, 2p+1) mod 3, so the
 //                  main loop of pair p+1 only waits for the epilogue of the FIRST half of pair p.
@@ -44,7 +47,8 @@ constexpr int kThreads = 192;
 constexpr int kEpiThreads = 128;
 constexpr int kTmemCols = 512;
 constexpr int kSlots = 3;
-constexpr int kMaxStages = 4;
+constexpr int kStagesA = 3;   // activation (halo box) ring
+constexpr int kMaxStagesB = 8;   // weight box ring
 
 struct KernelArgs {
     int B, H, W;
@@ -52,16 +56,17 @@ struct KernelArgs {
     int Cres, nchunks_res;     // residual K walk: nchunks_res stages (centre tap only)
     int N;
     int tiles_w, tiles_h, ntiles;
-    int nstages, stage_bytes;
+    int nstages_b, bbox_bytes; // weight ring: slots and bytes per slot (N x 128 B rounded up to 1 KiB)
     int slot_stride;           // TMEM columns between accumulator slots
     uint32_t idesc;
     ConvEpilogue ep;
 };
 
 // smem tail (after the 1024-aligned stage ring):
-//   uint64 full[4], empty[4], tfull[3], tempty[3]; uint32 tmem_slot[4];
+//   uint64 fullA[3], emptyA[3], fullB[8], emptyB[8], tfull[3], tempty[3]; uint32 tmem_slot[4];
 //   float bias[kMaxN], wres3[kMaxN*3], wfinal[3*kMaxN], bfinal[4]
-constexpr int kTailBytes = (2 * kMaxStages + 2 * kSlots) * 8 + 16 + (kMaxN + kMaxN * 3 + 3 * kMaxN + 4) * 4 + 64;
+constexpr int kTailBytes =
+    (2 * kStagesA + 2 * kMaxStagesB + 2 * kSlots) * 8 + 16 + (kMaxN + kMaxN * 3 + 3 * kMaxN + 4) * 4 + 64;
 
 __global__ void __launch_bounds__(kThreads, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_ares,
@@ -70,10 +75,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
-    uint8_t* tail = smem + (size_t)a.nstages * a.stage_bytes;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
-    uint64_t* empty_bar = full_bar + kMaxStages;
-    uint64_t* tfull_bar = empty_bar + kMaxStages;
+    uint8_t* smem_b = smem + (size_t)kStagesA * kABytes;
+    uint8_t* tail = smem_b + (size_t)a.nstages_b * a.bbox_bytes;
+    uint64_t* fulla_bar = reinterpret_cast<uint64_t*>(tail);
+    uint64_t* emptya_bar = fulla_bar + kStagesA;
+    uint64_t* fullb_bar = emptya_bar + kStagesA;
+    uint64_t* emptyb_bar = fullb_bar + kMaxStagesB;
+    uint64_t* tfull_bar = emptyb_bar + kMaxStagesB;
     uint64_t* tempty_bar = tfull_bar + kSlots;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + kSlots);
     float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
@@ -94,9 +102,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             tma_prefetch_desc(&tm_ares);
             tma_prefetch_desc(&tm_bres);
         }
-        for (int i = 0; i < a.nstages; ++i) {
-            mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], 1);
+        for (int i = 0; i < kStagesA; ++i) {
+            mbar_init(&fulla_bar[i], 1);
+            mbar_init(&emptya_bar[i], 1);
+        }
+        for (int i = 0; i < a.nstages_b; ++i) {
+            mbar_init(&fullb_bar[i], 1);
+            mbar_init(&emptyb_bar[i], 1);
         }
         for (int i = 0; i < kSlots; ++i) {
             mbar_init(&tfull_bar[i], 1);
@@ -130,43 +142,45 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     // elect their single issuing lane inside the asm (common.cuh) -- see elect_one_sync() for why.
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
-        int stage = 0;
-        uint32_t phase = 0;
+        int sa_i = 0, sb_i = 0;
+        uint32_t pha = 0, phb = 0;
         for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
             const int tw = tile % a.tiles_w;
             const int th = (tile / a.tiles_w) % a.tiles_h;
             const int b = tile / (a.tiles_w * a.tiles_h);
             const int h0 = th * kTileH, w0 = tw * kTileW;
             for (int it = 0; it < nst; ++it) {
-                mbar_wait(&empty_bar[stage], phase ^ 1u);
-                uint8_t* sa = smem + (size_t)stage * a.stage_bytes;
-                uint8_t* sb = sa + kABytes;
-                if (it < nst_main) {
-                    const int c = it / nkx;
-                    const int kx = it - c * nkx;
-                    mbar_arrive_expect_tx_w(&full_bar[stage], kABytes + (uint32_t)nky * nbytes);
-                    // rows h0-1 .. h0+16, columns shifted by the horizontal tap (centre column for 1x1)
-                    tma_load_4d_w(sa, &tm_a, &full_bar[stage], c * kKC, w0 + (nkx == 3 ? kx - 1 : 0), h0 - 1, b);
-                    for (int ky = 0; ky < nky; ++ky) {
-                        const int tap = nkx == 3 ? ky * 3 + kx : 0;
-                        tma_load_2d_w(sb + (size_t)ky * nbytes, &tm_b, &full_bar[stage], c * kKC, tap * N);
-                    }
-                } else {
-                    const int c = it - nst_main;
-                    mbar_arrive_expect_tx_w(&full_bar[stage], kABytes + nbytes);
-                    tma_load_4d_w(sa, &tm_ares, &full_bar[stage], c * kKC, w0, h0 - 1, b);
-                    tma_load_2d_w(sb, &tm_bres, &full_bar[stage], c * kKC, 0);
+                const bool main = it < nst_main;
+                const int c = main ? it / nkx : it - nst_main;
+                const int kx = main ? it - c * nkx : 0;
+                // activation halo box: rows h0-1 .. h0+16, columns shifted by the horizontal tap
+                mbar_wait(&emptya_bar[sa_i], pha ^ 1u);
+                mbar_arrive_expect_tx_w(&fulla_bar[sa_i], kABytes);
+                tma_load_4d_w(smem + (size_t)sa_i * kABytes, main ? &tm_a : &tm_ares, &fulla_bar[sa_i], c * kKC,
+                              w0 + ((main && nkx == 3) ? kx - 1 : 0), h0 - 1, b);
+                if (++sa_i == kStagesA) {
+                    sa_i = 0;
+                    pha ^= 1u;
                 }
-                if (++stage == a.nstages) {
-                    stage = 0;
-                    phase ^= 1u;
+                // weight boxes of the vertical taps that read this halo box
+                const int kys = main ? nky : 1;
+                for (int ky = 0; ky < kys; ++ky) {
+                    const int tap = (main && nkx == 3) ? ky * 3 + kx : 0;
+                    mbar_wait(&emptyb_bar[sb_i], phb ^ 1u);
+                    mbar_arrive_expect_tx_w(&fullb_bar[sb_i], nbytes);
+                    tma_load_2d_w(smem_b + (size_t)sb_i * a.bbox_bytes, main ? &tm_b : &tm_bres, &fullb_bar[sb_i],
+                                  c * kKC, tap * N);
+                    if (++sb_i == a.nstages_b) {
+                        sb_i = 0;
+                        phb ^= 1u;
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
-        int stage = 0;
-        uint32_t phase = 0;
+        int sa_i = 0, sb_i = 0;
+        uint32_t pha = 0, phb = 0;
         uint32_t slot_uses[kSlots] = {0, 0, 0};
         int titer = 0;
         // high 32 bits of every operand descriptor: SBO = 1024 B, version 1, 128B swizzle
@@ -182,29 +196,34 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             const uint32_t d0 = tmem_base + (uint32_t)(s0 * a.slot_stride);
             const uint32_t d1 = tmem_base + (uint32_t)(s1 * a.slot_stride);
             for (int it = 0; it < nst; ++it) {
-                mbar_wait(&full_bar[stage], phase);
-                tc_fence_after_sync();
-                const uint32_t sa = smem_u32(smem + (size_t)stage * a.stage_bytes);
-                const uint32_t sb = sa + kABytes;
                 const bool main = it < nst_main;
                 const int cvalid = main ? min(kKC, a.Cin - (it / nkx) * kKC) : min(kKC, a.Cres - (it - nst_main) * kKC);
                 const uint32_t nmma = (uint32_t)(cvalid >> 3);  // K = 8 tf32 per instruction, <= 4 per chunk
                 const int kys = main ? nky : 1;
+                mbar_wait(&fulla_bar[sa_i], pha);
+                const uint32_t sa = smem_u32(smem + (size_t)sa_i * kABytes);
                 for (int ky = 0; ky < kys; ++ky) {
+                    mbar_wait(&fullb_bar[sb_i], phb);
+                    tc_fence_after_sync();
                     // vertical tap = row offset into the halo box; the 1x1 / residual case reads the centre rows
                     const int row0 = (main && nky == 3) ? ky : 1;
                     const uint32_t a0 = ((sa + (uint32_t)row0 * kRowBytes) >> 4) & 0x3FFFu;
                     const uint32_t a1 = ((sa + (uint32_t)(row0 + 8) * kRowBytes) >> 4) & 0x3FFFu;
-                    const uint32_t bb = ((sb + (uint32_t)ky * nbytes) >> 4) & 0x3FFFu;
+                    const uint32_t bb = (smem_u32(smem_b + (size_t)sb_i * a.bbox_bytes) >> 4) & 0x3FFFu;
                     const uint32_t acc = (it | ky) != 0 ? 1u : 0u;
                     // K slices advance by 32 B inside the 128B-swizzled rows: +2 in the encoded start address
                     umma_tf32_ss_x4(d0, a0, bb, desc_hi, 2u, a.idesc, acc, nmma);
                     umma_tf32_ss_x4(d1, a1, bb, desc_hi, 2u, a.idesc, acc, nmma);
+                    umma_commit_elect(&emptyb_bar[sb_i]);
+                    if (++sb_i == a.nstages_b) {
+                        sb_i = 0;
+                        phb ^= 1u;
+                    }
                 }
-                umma_commit_elect(&empty_bar[stage]);
-                if (++stage == a.nstages) {
-                    stage = 0;
-                    phase ^= 1u;
+                umma_commit_elect(&emptya_bar[sa_i]);
+                if (++sa_i == kStagesA) {
+                    sa_i = 0;
+                    pha ^= 1u;
                 }
             }
             umma_commit_elect(&tfull_bar[s0]);
@@ -361,14 +380,14 @@ int tc_conv_prepare(const ConvProblem& p, TcConvOp* op) {
         op->tm_ares = op->tm_a;
         op->tm_bres = op->tm_b;
     }
-    const int nky = p.ntaps == 9 ? 3 : 1;
-    op->stage_bytes = kABytes + (int)align_up((size_t)nky * p.N * kKC * 4, 1024);
-    const int budget = device_info().max_smem_optin - 1024 /*alignment slack*/ - kTailBytes;
+    // weight ring: as many boxes as fit beside the 3 activation slots (at most kMaxStagesB)
+    op->stage_bytes = (int)align_up((size_t)p.N * kKC * 4, 1024);
+    const int budget = device_info().max_smem_optin - 1024 /*alignment slack*/ - kTailBytes - kStagesA * kABytes;
     int nst = budget / op->stage_bytes;
-    if (nst > kMaxStages) nst = kMaxStages;
-    SINDDM_REQUIRE(nst >= 2, "tc_conv: not enough shared memory for a 2-stage pipeline");
+    if (nst > kMaxStagesB) nst = kMaxStagesB;
+    SINDDM_REQUIRE(nst >= 3, "tc_conv: not enough shared memory for the weight ring");
     op->nstages = nst;
-    op->smem_bytes = nst * op->stage_bytes + kTailBytes + 1024;
+    op->smem_bytes = kStagesA * kABytes + nst * op->stage_bytes + kTailBytes + 1024;
     op->tiles_w = ceil_div(p.W, kTileW);
     op->tiles_h = ceil_div(p.H, kTileH);
     op->ntiles = op->tiles_w * op->tiles_h * p.B;
@@ -397,8 +416,8 @@ int tc_conv_launch(const TcConvOp& op, cudaStream_t stream) {
     a.tiles_w = op.tiles_w;
     a.tiles_h = op.tiles_h;
     a.ntiles = op.ntiles;
-    a.nstages = op.nstages;
-    a.stage_bytes = op.stage_bytes;
+    a.nstages_b = op.nstages;
+    a.bbox_bytes = op.stage_bytes;
     a.slot_stride = (int)align_up((size_t)p.N, 32);
     a.idesc = umma_idesc_tf32(128, p.N, 0, 0);
     a.ep = p.ep;
