@@ -23,8 +23,10 @@
 //   * operands land in 128B-swizzled K-major tiles that the UMMA descriptors consume directly.
 //   accumulators   fp32 in TMEM: three slots of N columns; tile pair p uses slots (2p, 2p+1) mod 3, so the
 //                  main loop of pair p+1 only waits for the epilogue of the FIRST half of pair p.
-//   roles          warp 0: TMA producer (one lane) | warp 1: TMEM alloc + MMA issue (one lane)
-//                  warps 2-5: epilogue (TMEM -> registers -> bias/residual/GELU/... -> global)
+//   roles          warp 0: TMA producer | warp 1: TMEM alloc + MMA issue (whole warps in uniform control flow,
+//                  the issuing lane is elected inside the asm: this removed a ~250-cycle/MMA issue cost)
+//                  warps 2-9: epilogue (TMEM -> registers -> bias/residual/GELU/... -> global), two warps per
+//                  TMEM lane quarter splitting the columns, global operands prefetched one chunk ahead
 //   grid           persistent, min(#tiles, #SMs) CTAs, static round-robin over tiles.
 #include <stdlib.h>
 #include <string.h>
@@ -43,8 +45,8 @@ constexpr int kKC = 32;                      // channels per K chunk (32 fp32 = 
 constexpr int kRowBytes = kTileW * kKC * 4;  // one image row of the box: 16 px x 128 B = 2 KiB
 constexpr int kABytes = kBoxH * kRowBytes;   // 36 KiB
 constexpr int kMaxN = 160;
-constexpr int kThreads = 192;
-constexpr int kEpiThreads = 128;
+constexpr int kThreads = 320;       // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr int kEpiThreads = 256;
 constexpr int kTmemCols = 512;
 constexpr int kSlots = 3;
 constexpr int kStagesA = 3;   // activation (halo box) ring
@@ -66,7 +68,7 @@ struct KernelArgs {
 //   uint64 fullA[3], emptyA[3], fullB[8], emptyB[8], tfull[3], tempty[3]; uint32 tmem_slot[4];
 //   float bias[kMaxN], wres3[kMaxN*3], wfinal[3*kMaxN], bfinal[4]
 constexpr int kTailBytes =
-    (2 * kStagesA + 2 * kMaxStagesB + 2 * kSlots) * 8 + 16 + (kMaxN + kMaxN * 3 + 3 * kMaxN + 4) * 4 + 64;
+    (2 * kStagesA + 2 * kMaxStagesB + 2 * kSlots) * 8 + 16 + (kMaxN + kMaxN * 3 + 3 * kMaxN + 4 + 128 * 3) * 4 + 64;
 
 __global__ void __launch_bounds__(kThreads, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_ares,
@@ -230,10 +232,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             umma_commit_elect(&tfull_bar[s1]);
         }
     } else {
-        // ------------------------------------------------------------ epilogue warps
-        const int quarter = warp & 3;             // TMEM lane quarter this warp may read
+        // ------------------------------------------------------------ epilogue warps (8)
+        // warp w reads TMEM lane quarter (w & 3); the two warps of a quarter split the 16-column chunks
+        // (even / odd), so a half tile is drained by 256 threads.
+        const int quarter = warp & 3;
+        const int cgrp = (warp - 2) >> 2;         // 0: chunks 0,2,4..  1: chunks 1,3,5..
         const int row = quarter * 32 + lane;      // accumulator row == pixel within the half tile
         const ConvEpilogue& ep = a.ep;
+        float* s_fin = reinterpret_cast<float*>(s_bfinal + 4);   // [128][3] partial final-conv sums of group 1
         uint32_t slot_uses[kSlots] = {0, 0, 0};
         int titer = 0;
         for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++titer) {
@@ -255,14 +261,39 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                 }
                 float fin[3] = {0.f, 0.f, 0.f};
 
+                // global operands of the first chunk are requested before the accumulator is even ready
+                const float* gsrc = ep.res_add ? ep.res_add : ep.dgelu_z;   // at most one streams per layer here
+                const float* gsrc2 = (ep.res_add && ep.dgelu_z) ? ep.dgelu_z : nullptr;
+                float4 pre[4], pre2[4];
+                int cc = cgrp * 16;
+                if (gsrc && valid && cc < N) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) pre[q] = __ldg(reinterpret_cast<const float4*>(gsrc + pix * N + cc) + q);
+                }
+
                 mbar_wait(&tfull_bar[slot], slot_uses[slot] & 1u);
                 ++slot_uses[slot];
                 tc_fence_after_sync();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(slot * a.slot_stride);
 
-                for (int cc = 0; cc < N; cc += 16) {
+                for (; cc < N; cc += 32) {
                     float v[16];
                     tmem_ld16(taddr + cc, v);
+                    float4 cur[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) cur[q] = pre[q];
+                    const size_t off = pix * N + cc;
+                    if (valid) {
+                        if (gsrc && cc + 32 < N) {   // prefetch the next chunk of this warp
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                pre[q] = __ldg(reinterpret_cast<const float4*>(gsrc + off + 32) + q);
+                        }
+                        if (gsrc2) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) pre2[q] = __ldg(reinterpret_cast<const float4*>(gsrc2 + off) + q);
+                        }
+                    }
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] += s_bias[cc + j];
                     if (ep.w_res3) {
@@ -273,18 +304,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                         }
                     }
                     if (valid) {
-                        const size_t off = pix * N + cc;
                         if (ep.res_add) {
-                            const float4* r4 = reinterpret_cast<const float4*>(ep.res_add + off);
-                            float4 r[4];
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) r[q] = __ldg(r4 + q);
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
-                                v[4 * q + 0] += r[q].x;
-                                v[4 * q + 1] += r[q].y;
-                                v[4 * q + 2] += r[q].z;
-                                v[4 * q + 3] += r[q].w;
+                                v[4 * q + 0] += cur[q].x;
+                                v[4 * q + 1] += cur[q].y;
+                                v[4 * q + 2] += cur[q].z;
+                                v[4 * q + 3] += cur[q].w;
                             }
                         }
                         if (ep.out_pre) {
@@ -295,19 +321,16 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                         }
                         if (ep.gelu) {
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
+                            for (int j = 0; j < 16; ++j) v[j] = gelu_fast(v[j]);
                         }
                         if (ep.dgelu_z) {
-                            const float4* z4 = reinterpret_cast<const float4*>(ep.dgelu_z + off);
-                            float4 z[4];
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) z[q] = __ldg(z4 + q);
+                            const float4* z = gsrc2 ? pre2 : cur;
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
-                                v[4 * q + 0] *= gelu_erf_grad(z[q].x);
-                                v[4 * q + 1] *= gelu_erf_grad(z[q].y);
-                                v[4 * q + 2] *= gelu_erf_grad(z[q].z);
-                                v[4 * q + 3] *= gelu_erf_grad(z[q].w);
+                                v[4 * q + 0] *= gelu_grad_fast(z[q].x);
+                                v[4 * q + 1] *= gelu_grad_fast(z[q].y);
+                                v[4 * q + 2] *= gelu_grad_fast(z[q].z);
+                                v[4 * q + 3] *= gelu_grad_fast(z[q].w);
                             }
                         }
                         if (ep.w_final) {
@@ -334,12 +357,22 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                 tc_fence_before_sync();
                 mbar_arrive(&tempty_bar[slot]);
 
-                if (ep.w_final && valid) {
-                    const size_t plane = (size_t)a.H * a.W;
-                    float* o = ep.out_final + (size_t)b * 3 * plane + (size_t)h * a.W + w;
-                    o[0] = fin[0] + s_bfinal[0];
-                    o[plane] = fin[1] + s_bfinal[1];
-                    o[2 * plane] = fin[2] + s_bfinal[2];
+                if (ep.w_final) {
+                    // the two column groups of a pixel combine their partial 3-channel sums through smem
+                    if (cgrp == 1) {
+                        s_fin[row * 3 + 0] = fin[0];
+                        s_fin[row * 3 + 1] = fin[1];
+                        s_fin[row * 3 + 2] = fin[2];
+                    }
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    if (cgrp == 0 && valid) {
+                        const size_t plane = (size_t)a.H * a.W;
+                        float* o = ep.out_final + (size_t)b * 3 * plane + (size_t)h * a.W + w;
+                        o[0] = fin[0] + s_fin[row * 3 + 0] + s_bfinal[0];
+                        o[plane] = fin[1] + s_fin[row * 3 + 1] + s_bfinal[1];
+                        o[2 * plane] = fin[2] + s_fin[row * 3 + 2] + s_bfinal[2];
+                    }
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
                 }
             }
         }
