@@ -276,9 +276,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                 tc_fence_after_sync();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(slot * a.slot_stride);
 
-                for (; cc < N; cc += 32) {
+                // TMEM -> register loads are double buffered: chunk i+1 is in flight while chunk i is processed
+                auto process = [&](const int cc, const uint32_t (&raw)[16]) {
                     float v[16];
-                    tmem_ld16(taddr + cc, v);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
                     float4 cur[4];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) cur[q] = pre[q];
@@ -352,8 +354,23 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                                 o4[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
                         }
                     }
+                };
+                {
+                    uint32_t r0[16], r1[16];
+                    if (cc < N) tmem_ld16_issue(taddr + cc, r0);
+                    while (cc < N) {
+                        tmem_ld16_wait(r0);
+                        if (cc + 32 < N) tmem_ld16_issue(taddr + cc + 32, r1);
+                        process(cc, r0);
+                        cc += 32;
+                        if (cc >= N) break;
+                        tmem_ld16_wait(r1);
+                        if (cc + 32 < N) tmem_ld16_issue(taddr + cc + 32, r0);
+                        process(cc, r1);
+                        cc += 32;
+                    }
                 }
-                // every tcgen05.ld of this slot has completed (wait::ld inside tmem_ld16): hand it back
+                // every tcgen05.ld of this slot has completed (tmem_ld16_wait): hand it back
                 tc_fence_before_sync();
                 mbar_arrive(&tempty_bar[slot]);
 
