@@ -363,6 +363,126 @@ SINDDM_DEVINL void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// ----------------------------------------------------------------------------------------------
+// CTA-pair (cta_group::2) variants: two CTAs of a cluster run ONE M=256 MMA; each supplies its own 128 rows
+// of A and half of the rows of B from its own shared memory and keeps its 128 accumulator rows in its own
+// TMEM.  Only the leader CTA (cluster rank 0) issues MMAs; TMA loads of both CTAs complete on the leader's
+// mbarrier (same smem offset, peer bit cleared), commits multicast to both CTAs' barriers.
+// ----------------------------------------------------------------------------------------------
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // shared::cluster address of "the same offset in the even CTA"
+
+SINDDM_DEVINL void tmem_alloc_2sm(uint32_t* smem_slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+
+SINDDM_DEVINL void tmem_dealloc_2sm(uint32_t tmem_addr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_addr), "r"(ncols) : "memory");
+}
+
+SINDDM_DEVINL void tma_load_2d_2sm_w(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "{\n\t.reg .pred pe;\n\t.reg .b32 rx;\n\telect.sync rx|pe, 0xffffffff;\n\t"
+        "@pe cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], "
+        "[%1, {%3, %4}], [%2];\n\t}\n" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+SINDDM_DEVINL void tma_load_4d_2sm_w(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                     int c3) {
+    asm volatile(
+        "{\n\t.reg .pred pe;\n\t.reg .b32 rx;\n\telect.sync rx|pe, 0xffffffff;\n\t"
+        "@pe cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], "
+        "[%1, {%3, %4, %5, %6}], [%2];\n\t}\n" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
+// arrive (no transaction bytes) on the barrier at this smem offset in CTA `cta` of the cluster
+SINDDM_DEVINL void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(smem_u32(bar)),
+        "r"(cta)
+        : "memory");
+}
+
+SINDDM_DEVINL void mbar_arrive_remote_w(uint64_t* bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t.reg .pred pe;\n\t.reg .b32 rx, ra;\n\telect.sync rx|pe, 0xffffffff;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "@pe mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(smem_u32(bar)),
+        "r"(cta)
+        : "memory");
+}
+
+// cluster-scope acquire wait (the barrier is arrived on by the peer CTA)
+SINDDM_DEVINL void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+
+SINDDM_DEVINL void umma_tf32_ss_x4_2sm(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t step_lo,
+                                       uint32_t idesc, uint32_t acc_first, uint32_t nk) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pe, pacc, pone, p1, p2, p3;\n\t"
+        ".reg .b32 rx, a1, a2, a3, b1, b2, b3;\n\t"
+        ".reg .b64 da0, da1, da2, da3, db0, db1, db2, db3;\n\t"
+        "elect.sync rx|pe, 0xffffffff;\n\t"
+        "setp.ne.b32 pacc, %6, 0;\n\t"
+        "setp.eq.b32 pone, 0, 0;\n\t"
+        "setp.gt.u32 p1, %7, 1;\n\t"
+        "setp.gt.u32 p2, %7, 2;\n\t"
+        "setp.gt.u32 p3, %7, 3;\n\t"
+        "and.pred p1, p1, pe;\n\t"
+        "and.pred p2, p2, pe;\n\t"
+        "and.pred p3, p3, pe;\n\t"
+        "add.u32 a1, %1, %4;\n\t"
+        "add.u32 a2, a1, %4;\n\t"
+        "add.u32 a3, a2, %4;\n\t"
+        "add.u32 b1, %2, %4;\n\t"
+        "add.u32 b2, b1, %4;\n\t"
+        "add.u32 b3, b2, %4;\n\t"
+        "mov.b64 da0, {%1, %3};\n\t"
+        "mov.b64 da1, {a1, %3};\n\t"
+        "mov.b64 da2, {a2, %3};\n\t"
+        "mov.b64 da3, {a3, %3};\n\t"
+        "mov.b64 db0, {%2, %3};\n\t"
+        "mov.b64 db1, {b1, %3};\n\t"
+        "mov.b64 db2, {b2, %3};\n\t"
+        "mov.b64 db3, {b3, %3};\n\t"
+        "@pe tcgen05.mma.cta_group::2.kind::tf32 [%0], da0, db0, %5, pacc;\n\t"
+        "@p1 tcgen05.mma.cta_group::2.kind::tf32 [%0], da1, db1, %5, pone;\n\t"
+        "@p2 tcgen05.mma.cta_group::2.kind::tf32 [%0], da2, db2, %5, pone;\n\t"
+        "@p3 tcgen05.mma.cta_group::2.kind::tf32 [%0], da3, db3, %5, pone;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(hi), "r"(step_lo), "r"(idesc), "r"(acc_first), "r"(nk)
+        : "memory");
+}
+
+// leader CTA: arrive on the barrier at this offset in both CTAs of the pair once all prior MMAs are done
+SINDDM_DEVINL void umma_commit_2sm_elect(uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .pred pe;\n\t.reg .b32 rx;\n\telect.sync rx|pe, 0xffffffff;\n\t"
+        "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}\n" ::
+            "r"(smem_u32(bar)),
+        "h"((uint16_t)3)
+        : "memory");
+}
+
 // Split version for software pipelining: issue the load, do other work, then wait.  The wait takes the
 // destination registers as in/out operands so the compiler cannot move their first use above it.
 SINDDM_DEVINL void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {

@@ -70,6 +70,9 @@ struct KernelArgs {
 constexpr int kTailBytes =
     (2 * kStagesA + 2 * kMaxStagesB + 2 * kSlots) * 8 + 16 + (kMaxN + kMaxN * 3 + 3 * kMaxN + 4 + 128 * 3) * 4 + 64;
 
+// TWO = true: CTA pairs (cluster of 2, cta_group::2): one M=256 MMA covers the same half of BOTH CTAs' tiles,
+// each CTA stages only half of the weight rows, and only the leader CTA issues MMAs.
+template <bool TWO>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_ares,
                const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_bres,
@@ -105,20 +108,23 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             tma_prefetch_desc(&tm_bres);
         }
         for (int i = 0; i < kStagesA; ++i) {
-            mbar_init(&fulla_bar[i], 1);
+            mbar_init(&fulla_bar[i], TWO ? 2 : 1);   // one arrival per producing CTA
             mbar_init(&emptya_bar[i], 1);
         }
         for (int i = 0; i < a.nstages_b; ++i) {
-            mbar_init(&fullb_bar[i], 1);
+            mbar_init(&fullb_bar[i], TWO ? 2 : 1);
             mbar_init(&emptyb_bar[i], 1);
         }
         for (int i = 0; i < kSlots; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], kEpiThreads);
+            mbar_init(&tempty_bar[i], (TWO ? 2 : 1) * (kEpiThreads / 32));   // one arrival per epilogue warp
         }
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+    if (warp == 1) {
+        if (TWO) tmem_alloc_2sm(tmem_slot, kTmemCols);
+        else tmem_alloc(tmem_slot, kTmemCols);
+    }
     if (warp >= 2) {
         const int t = threadIdx.x - 64;
         for (int i = t; i < N; i += kEpiThreads) s_bias[i] = a.ep.bias ? a.ep.bias[i] : 0.f;
@@ -131,14 +137,20 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     }
     tc_fence_before_sync();
     __syncthreads();
+    if (TWO) cluster_sync_all();   // both CTAs' barriers and TMEM exist before any cross-CTA traffic
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    constexpr int CS = TWO ? 2 : 1;
+    const int crank = TWO ? (int)cluster_ctarank() : 0;
+    const int pair_id = blockIdx.x / CS;
+    const int npairs = gridDim.x / CS;
+    const int nsuper = (a.ntiles + CS - 1) / CS;
 
     const int nkx = a.ntaps == 9 ? 3 : 1;           // horizontal taps = stages per chunk
     const int nky = nkx;                             // vertical taps = weight boxes per stage
     const int nst_main = a.nchunks * nkx;
     const int nst = nst_main + a.nchunks_res;        // stages per tile
-    const uint32_t nbytes = (uint32_t)N * kKC * 4;   // one weight box
+    const uint32_t nbytes = (uint32_t)(N / CS) * kKC * 4;   // one weight box as staged by THIS CTA
 
     // Roles 0 and 1 run their loops with ALL 32 lanes (uniform control flow); TMA, MMA and commit instructions
     // elect their single issuing lane inside the asm (common.cuh) -- see elect_one_sync() for why.
@@ -146,7 +158,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         // ------------------------------------------------------------ TMA producer
         int sa_i = 0, sb_i = 0;
         uint32_t pha = 0, phb = 0;
-        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        for (int st = pair_id; st < nsuper; st += npairs) {
+            // a tile index past the end (odd tile count, second CTA of the last pair) runs the same pipeline on
+            // zeros: image index >= B is out of bounds for TMA, which zero-fills the box
+            const int tile = st * CS + crank;
             const int tw = tile % a.tiles_w;
             const int th = (tile / a.tiles_w) % a.tiles_h;
             const int b = tile / (a.tiles_w * a.tiles_h);
@@ -157,9 +172,17 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                 const int kx = main ? it - c * nkx : 0;
                 // activation halo box: rows h0-1 .. h0+16, columns shifted by the horizontal tap
                 mbar_wait(&emptya_bar[sa_i], pha ^ 1u);
-                mbar_arrive_expect_tx_w(&fulla_bar[sa_i], kABytes);
-                tma_load_4d_w(smem + (size_t)sa_i * kABytes, main ? &tm_a : &tm_ares, &fulla_bar[sa_i], c * kKC,
-                              w0 + ((main && nkx == 3) ? kx - 1 : 0), h0 - 1, b);
+                if (!TWO) {
+                    mbar_arrive_expect_tx_w(&fulla_bar[sa_i], kABytes);
+                    tma_load_4d_w(smem + (size_t)sa_i * kABytes, main ? &tm_a : &tm_ares, &fulla_bar[sa_i], c * kKC,
+                                  w0 + ((main && nkx == 3) ? kx - 1 : 0), h0 - 1, b);
+                } else {
+                    // both CTAs' boxes complete on the LEADER's barrier, which expects the bytes of both
+                    if (crank == 0) mbar_arrive_expect_tx_w(&fulla_bar[sa_i], 2 * kABytes);
+                    else mbar_arrive_remote_w(&fulla_bar[sa_i], 0);
+                    tma_load_4d_2sm_w(smem + (size_t)sa_i * kABytes, main ? &tm_a : &tm_ares, &fulla_bar[sa_i], c * kKC,
+                                      w0 + ((main && nkx == 3) ? kx - 1 : 0), h0 - 1, b);
+                }
                 if (++sa_i == kStagesA) {
                     sa_i = 0;
                     pha ^= 1u;
@@ -169,9 +192,17 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                 for (int ky = 0; ky < kys; ++ky) {
                     const int tap = (main && nkx == 3) ? ky * 3 + kx : 0;
                     mbar_wait(&emptyb_bar[sb_i], phb ^ 1u);
-                    mbar_arrive_expect_tx_w(&fullb_bar[sb_i], nbytes);
-                    tma_load_2d_w(smem_b + (size_t)sb_i * a.bbox_bytes, main ? &tm_b : &tm_bres, &fullb_bar[sb_i],
-                                  c * kKC, tap * N);
+                    if (!TWO) {
+                        mbar_arrive_expect_tx_w(&fullb_bar[sb_i], nbytes);
+                        tma_load_2d_w(smem_b + (size_t)sb_i * a.bbox_bytes, main ? &tm_b : &tm_bres, &fullb_bar[sb_i],
+                                      c * kKC, tap * N);
+                    } else {
+                        // this CTA stages rows [crank*N/2, (crank+1)*N/2) of the tap's weight matrix
+                        if (crank == 0) mbar_arrive_expect_tx_w(&fullb_bar[sb_i], 2 * nbytes);
+                        else mbar_arrive_remote_w(&fullb_bar[sb_i], 0);
+                        tma_load_2d_2sm_w(smem_b + (size_t)sb_i * a.bbox_bytes, main ? &tm_b : &tm_bres,
+                                          &fullb_bar[sb_i], c * kKC, tap * N + crank * (N / 2));
+                    }
                     if (++sb_i == a.nstages_b) {
                         sb_i = 0;
                         phb ^= 1u;
@@ -179,19 +210,24 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                 }
             }
         }
-    } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer
+    } else if (warp == 1 && crank == 0) {
+        // ------------------------------------------------------------ MMA issuer (leader CTA of a pair)
         int sa_i = 0, sb_i = 0;
         uint32_t pha = 0, phb = 0;
         uint32_t slot_uses[kSlots] = {0, 0, 0};
         int titer = 0;
         // high 32 bits of every operand descriptor: SBO = 1024 B, version 1, 128B swizzle
         const uint32_t desc_hi = (uint32_t)(umma_smem_desc(0, 0, 1024, UMMA_LAYOUT_SW128) >> 32);
-        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++titer) {
+        for (int st = pair_id; st < nsuper; st += npairs, ++titer) {
             const int s0 = (2 * titer) % kSlots, s1 = (2 * titer + 1) % kSlots;
-            // the slot must have been drained by the epilogue of its previous use
-            mbar_wait(&tempty_bar[s0], (slot_uses[s0] & 1u) ^ 1u);
-            mbar_wait(&tempty_bar[s1], (slot_uses[s1] & 1u) ^ 1u);
+            // the slot must have been drained by the epilogue (of both CTAs) of its previous use
+            if (TWO) {
+                mbar_wait_cluster(&tempty_bar[s0], (slot_uses[s0] & 1u) ^ 1u);
+                mbar_wait_cluster(&tempty_bar[s1], (slot_uses[s1] & 1u) ^ 1u);
+            } else {
+                mbar_wait(&tempty_bar[s0], (slot_uses[s0] & 1u) ^ 1u);
+                mbar_wait(&tempty_bar[s1], (slot_uses[s1] & 1u) ^ 1u);
+            }
             ++slot_uses[s0];
             ++slot_uses[s1];
             tc_fence_after_sync();
@@ -214,24 +250,36 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                     const uint32_t bb = (smem_u32(smem_b + (size_t)sb_i * a.bbox_bytes) >> 4) & 0x3FFFu;
                     const uint32_t acc = (it | ky) != 0 ? 1u : 0u;
                     // K slices advance by 32 B inside the 128B-swizzled rows: +2 in the encoded start address
-                    umma_tf32_ss_x4(d0, a0, bb, desc_hi, 2u, a.idesc, acc, nmma);
-                    umma_tf32_ss_x4(d1, a1, bb, desc_hi, 2u, a.idesc, acc, nmma);
-                    umma_commit_elect(&emptyb_bar[sb_i]);
+                    if (TWO) {
+                        umma_tf32_ss_x4_2sm(d0, a0, bb, desc_hi, 2u, a.idesc, acc, nmma);
+                        umma_tf32_ss_x4_2sm(d1, a1, bb, desc_hi, 2u, a.idesc, acc, nmma);
+                        umma_commit_2sm_elect(&emptyb_bar[sb_i]);
+                    } else {
+                        umma_tf32_ss_x4(d0, a0, bb, desc_hi, 2u, a.idesc, acc, nmma);
+                        umma_tf32_ss_x4(d1, a1, bb, desc_hi, 2u, a.idesc, acc, nmma);
+                        umma_commit_elect(&emptyb_bar[sb_i]);
+                    }
                     if (++sb_i == a.nstages_b) {
                         sb_i = 0;
                         phb ^= 1u;
                     }
                 }
-                umma_commit_elect(&emptya_bar[sa_i]);
+                if (TWO) umma_commit_2sm_elect(&emptya_bar[sa_i]);
+                else umma_commit_elect(&emptya_bar[sa_i]);
                 if (++sa_i == kStagesA) {
                     sa_i = 0;
                     pha ^= 1u;
                 }
             }
-            umma_commit_elect(&tfull_bar[s0]);
-            umma_commit_elect(&tfull_bar[s1]);
+            if (TWO) {
+                umma_commit_2sm_elect(&tfull_bar[s0]);
+                umma_commit_2sm_elect(&tfull_bar[s1]);
+            } else {
+                umma_commit_elect(&tfull_bar[s0]);
+                umma_commit_elect(&tfull_bar[s1]);
+            }
         }
-    } else {
+    } else if (warp >= 2) {
         // ------------------------------------------------------------ epilogue warps (8)
         // warp w reads TMEM lane quarter (w & 3); the two warps of a quarter split the 16-column chunks
         // (even / odd), so a half tile is drained by 256 threads.
@@ -242,7 +290,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         float* s_fin = reinterpret_cast<float*>(s_bfinal + 4);   // [128][3] partial final-conv sums of group 1
         uint32_t slot_uses[kSlots] = {0, 0, 0};
         int titer = 0;
-        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++titer) {
+        for (int st = pair_id; st < nsuper; st += npairs, ++titer) {
+            const int tile = st * CS + crank;
             const int tw = tile % a.tiles_w;
             const int th = (tile / a.tiles_w) % a.tiles_h;
             const int b = tile / (a.tiles_w * a.tiles_h);
@@ -250,7 +299,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             for (int half = 0; half < 2; ++half) {
                 const int slot = (2 * titer + half) % kSlots;
                 const int h = th * kTileH + half * 8 + row / kTileW, w = tw * kTileW + row % kTileW;
-                const bool valid = (h < a.H) && (w < a.W);
+                const bool valid = (tile < a.ntiles) && (h < a.H) && (w < a.W);
                 const size_t pix = ((size_t)b * a.H + h) * a.W + w;
 
                 float x3v[3] = {0.f, 0.f, 0.f};
@@ -372,7 +421,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                 }
                 // every tcgen05.ld of this slot has completed (tmem_ld16_wait): hand it back
                 tc_fence_before_sync();
-                mbar_arrive(&tempty_bar[slot]);
+                __syncwarp();
+                if (lane == 0) {
+                    if (TWO) mbar_arrive_remote(&tempty_bar[slot], 0);   // the leader's MMA warp waits for both CTAs
+                    else mbar_arrive(&tempty_bar[slot]);
+                }
 
                 if (ep.w_final) {
                     // the two column groups of a pixel combine their partial 3-channel sums through smem
@@ -398,13 +451,24 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     // ---------------------------------------------------------------- teardown
     tc_fence_before_sync();
     __syncthreads();
+    if (TWO) cluster_sync_all();   // neither CTA leaves while the other may still touch its smem / TMEM
     if (warp == 1) {
         tc_fence_after_sync();
-        tmem_dealloc(tmem_base, kTmemCols);
+        if (TWO) tmem_dealloc_2sm(tmem_base, kTmemCols);
+        else tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
 }  // namespace
+
+static int two_sm_setting() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SINDDM_TC_2SM");
+        v = e ? (atoi(e) != 0) : 1;
+    }
+    return v;
+}
 
 bool tc_conv_supported(const ConvProblem& p) {
     if (p.Cin < 8 || p.Cin % 8 != 0) return false;
@@ -419,19 +483,21 @@ int tc_conv_prepare(const ConvProblem& p, TcConvOp* op) {
                    p.N, p.ntaps);
     SINDDM_REQUIRE(device_info().initialized, "sinddm_init() has not been called");
     op->p = p;
-    op->cs = 1;
+    // CTA pairs (SINDDM_TC_2SM=0 disables): each CTA stages N/2 weight rows, which must be whole 8-row atoms
+    op->cs = (two_sm_setting() && p.N % 16 == 0) ? 2 : 1;
+    const int cs = op->cs;
     SINDDM_TRY(make_tmap_nhwc(&op->tm_a, p.in, p.B, p.H, p.W, p.Cin, kKC, kTileW, kBoxH, CU_TENSOR_MAP_SWIZZLE_128B));
-    SINDDM_TRY(make_tmap_2d(&op->tm_b, p.w, p.Cin, p.ntaps * p.N, kKC, p.N, CU_TENSOR_MAP_SWIZZLE_128B));
+    SINDDM_TRY(make_tmap_2d(&op->tm_b, p.w, p.Cin, p.ntaps * p.N, kKC, p.N / cs, CU_TENSOR_MAP_SWIZZLE_128B));
     if (p.in_res) {
         SINDDM_TRY(make_tmap_nhwc(&op->tm_ares, p.in_res, p.B, p.H, p.W, p.Cres, kKC, kTileW, kBoxH,
                                   CU_TENSOR_MAP_SWIZZLE_128B));
-        SINDDM_TRY(make_tmap_2d(&op->tm_bres, p.w_res, p.Cres, p.N, kKC, p.N, CU_TENSOR_MAP_SWIZZLE_128B));
+        SINDDM_TRY(make_tmap_2d(&op->tm_bres, p.w_res, p.Cres, p.N, kKC, p.N / cs, CU_TENSOR_MAP_SWIZZLE_128B));
     } else {
         op->tm_ares = op->tm_a;
         op->tm_bres = op->tm_b;
     }
     // weight ring: as many boxes as fit beside the 3 activation slots (at most kMaxStagesB)
-    op->stage_bytes = (int)align_up((size_t)p.N * kKC * 4, 1024);
+    op->stage_bytes = (int)align_up((size_t)(p.N / cs) * kKC * 4, 1024);
     const int budget = device_info().max_smem_optin - 1024 /*alignment slack*/ - kTailBytes - kStagesA * kABytes;
     int nst = budget / op->stage_bytes;
     if (nst > kMaxStagesB) nst = kMaxStagesB;
@@ -441,14 +507,19 @@ int tc_conv_prepare(const ConvProblem& p, TcConvOp* op) {
     op->tiles_w = ceil_div(p.W, kTileW);
     op->tiles_h = ceil_div(p.H, kTileH);
     op->ntiles = op->tiles_w * op->tiles_h * p.B;
-    op->grid = op->ntiles < device_info().num_sms ? op->ntiles : device_info().num_sms;
+    const int nsuper = ceil_div(op->ntiles, cs);
+    int npairs = device_info().num_sms / cs;
+    if (npairs > nsuper) npairs = nsuper;
+    op->grid = npairs * cs;
     return SINDDM_OK;
 }
 
 int tc_conv_launch(const TcConvOp& op, cudaStream_t stream) {
     static int smem_set = 0;
     if (!smem_set) {
-        SINDDM_CUDA_OK(cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        SINDDM_CUDA_OK(cudaFuncSetAttribute(tc_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            device_info().max_smem_optin));
+        SINDDM_CUDA_OK(cudaFuncSetAttribute(tc_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             device_info().max_smem_optin));
         smem_set = 1;
     }
@@ -469,11 +540,33 @@ int tc_conv_launch(const TcConvOp& op, cudaStream_t stream) {
     a.nstages_b = op.nstages;
     a.bbox_bytes = op.stage_bytes;
     a.slot_stride = (int)align_up((size_t)p.N, 32);
-    a.idesc = umma_idesc_tf32(128, p.N, 0, 0);
+    a.idesc = umma_idesc_tf32(op.cs == 2 ? 256 : 128, p.N, 0, 0);
     a.ep = p.ep;
     // algorithmic work: real pixels x N x (taps*Cin + Cres) MACs
     prof_begin(stream, 0, 2.0 * (double)p.B * p.H * p.W * p.N * ((double)p.ntaps * p.Cin + a.Cres));
-    tc_conv_kernel<<<op.grid, kThreads, op.smem_bytes, stream>>>(op.tm_a, op.tm_ares, op.tm_b, op.tm_bres, a);
+    if (op.cs == 2) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(op.grid);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = op.smem_bytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t lerr = cudaLaunchKernelEx(&cfg, tc_conv_kernel<true>, op.tm_a, op.tm_ares, op.tm_b, op.tm_bres, a);
+        if (lerr != cudaSuccess) {
+            prof_end(stream);
+            set_error("tc_conv (cta pair) launch failed: %s", cudaGetErrorString(lerr));
+            return SINDDM_ERR_CUDA;
+        }
+    } else {
+        tc_conv_kernel<false><<<op.grid, kThreads, op.smem_bytes, stream>>>(op.tm_a, op.tm_ares, op.tm_b, op.tm_bres, a);
+    }
     prof_end(stream);
     SINDDM_CUDA_OK(cudaGetLastError());
     return SINDDM_OK;
