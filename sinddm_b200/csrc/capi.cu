@@ -77,6 +77,7 @@ int sinddm_conv_forward(const sinddm_conv_desc* d, int math, void* stream) {
     p.B = d->B; p.H = d->H; p.W = d->W;
     p.in = d->in; p.Cin = d->Cin; p.w = d->w; p.ntaps = d->ntaps;
     p.in_res = d->in_res; p.Cres = d->Cres; p.w_res = d->w_res; p.N = d->N;
+    p.w_blocked = 0;
     p.ep.bias = d->bias; p.ep.res_add = d->res_add; p.ep.x3 = d->x3; p.ep.w_res3 = d->w_res3;
     p.ep.gelu = d->gelu; p.ep.out_pre = d->out_pre; p.ep.dgelu_z = d->dgelu_z;
     p.ep.w_final = d->w_final; p.ep.b_final = d->b_final; p.ep.out_final = d->out_final;

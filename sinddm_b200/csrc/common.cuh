@@ -193,6 +193,18 @@ SINDDM_DEVINL void tma_load_4d_w(void* smem_dst, const CUtensorMap* map, uint64_
         : "memory");
 }
 
+// 1-D bulk copy global -> shared of `bytes` contiguous bytes (multiple of 16, both addresses 16-byte aligned),
+// completing on an mbarrier like a tensor copy.  One request stream of full lines instead of one 128-byte
+// row per tensor-box row.
+SINDDM_DEVINL void bulk_copy_g2s_w(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .pred pe;\n\t.reg .b32 rx;\n\telect.sync rx|pe, 0xffffffff;\n\t"
+        "@pe cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}\n" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
 // Multicast variant: the box is written at the same CTA-relative smem offset of every CTA in `cta_mask`
 // and completes bytes on the mbarrier at the same offset in each of them.
 SINDDM_DEVINL void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,

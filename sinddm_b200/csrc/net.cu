@@ -12,6 +12,7 @@
 // (Cin >= 8 and N % 16 == 0); the 3-channel layers and math == MATH_FP32 use the CUDA-core twin.
 #include "net.h"
 
+#include <stdlib.h>
 #include <string.h>
 
 namespace sinddm {
@@ -86,12 +87,13 @@ size_t carve(Plan* pl, uint8_t* base) {
         BlockBufs& b = pl->blk[l];
         block_channels(l, dim, ch, &b.Ci, &b.Co);
         b.has_res = b.Ci != b.Co;
-        b.w0_f = cv.take((size_t)9 * b.Co * b.Ci);
-        b.w2_f = cv.take((size_t)9 * b.Co * b.Co);
-        b.wr_f = b.has_res ? cv.take((size_t)b.Co * b.Ci) : nullptr;
-        b.w0_d = tr ? cv.take((size_t)9 * b.Co * b.Ci) : nullptr;
-        b.w2_d = tr ? cv.take((size_t)9 * b.Co * b.Co) : nullptr;
-        b.wr_d = (tr && b.has_res) ? cv.take((size_t)b.Co * b.Ci) : nullptr;
+        // packed weights (sized for the blocked layout: K padded to a multiple of 32)
+        b.w0_f = cv.take(packed_weight_floats(9, b.Co, b.Ci));
+        b.w2_f = cv.take(packed_weight_floats(9, b.Co, b.Co));
+        b.wr_f = b.has_res ? cv.take(packed_weight_floats(1, b.Co, b.Ci)) : nullptr;
+        b.w0_d = tr ? cv.take(packed_weight_floats(9, b.Ci, b.Co)) : nullptr;
+        b.w2_d = tr ? cv.take(packed_weight_floats(9, b.Co, b.Co)) : nullptr;
+        b.wr_d = (tr && b.has_res) ? cv.take(packed_weight_floats(1, b.Ci, b.Co)) : nullptr;
         b.bias2c = b.has_res ? cv.take((size_t)b.Co) : nullptr;
         if (tr) {
             b.h0 = cv.take(P * b.Ci);
@@ -200,6 +202,19 @@ int plan_build(Plan* pl, int B, int H, int W, int dim, int channels, int math, i
     pl->ws = static_cast<float*>(ws);
     pl->ws_bytes = ws_bytes;
     carve(pl, static_cast<uint8_t*>(ws));
+    // blocked weight boxes are padded to 32 channels: the padding must read as zero, so clear the packed-weight
+    // buffers once (the pack kernels only ever write real elements)
+    const char* e2sm = getenv("SINDDM_TC_2SM");
+    pl->blocked_weights = (math == MATH_TF32) && !(e2sm && atoi(e2sm) != 0);
+    for (int l = 0; l < kNumBlocks; ++l) {
+        BlockBufs& b = pl->blk[l];
+        SINDDM_CUDA_OK(cudaMemset(b.w0_f, 0, packed_weight_floats(9, b.Co, b.Ci) * sizeof(float)));
+        SINDDM_CUDA_OK(cudaMemset(b.w2_f, 0, packed_weight_floats(9, b.Co, b.Co) * sizeof(float)));
+        if (b.wr_f) SINDDM_CUDA_OK(cudaMemset(b.wr_f, 0, packed_weight_floats(1, b.Co, b.Ci) * sizeof(float)));
+        if (b.w0_d) SINDDM_CUDA_OK(cudaMemset(b.w0_d, 0, packed_weight_floats(9, b.Ci, b.Co) * sizeof(float)));
+        if (b.w2_d) SINDDM_CUDA_OK(cudaMemset(b.w2_d, 0, packed_weight_floats(9, b.Co, b.Co) * sizeof(float)));
+        if (b.wr_d) SINDDM_CUDA_OK(cudaMemset(b.wr_d, 0, packed_weight_floats(1, b.Ci, b.Co) * sizeof(float)));
+    }
 
     const bool tr = training != 0;
     const int rnd = math == MATH_TF32 ? 1 : 0;
@@ -219,6 +234,7 @@ int plan_build(Plan* pl, int B, int H, int W, int dim, int channels, int math, i
         b.tc_c1 = use_tc_conv(math, b.Ci, 0, false, b.Co);
         b.tc_c2 = use_tc_conv(math, b.Co, b.Ci, res_slices, b.Co);
         c1.ep.gelu = 1; c1.ep.out = b.a1; c1.ep.out_pre = tr ? b.z1 : nullptr; c1.ep.round_tf32 = rnd && b.tc_c2;
+        c1.w_blocked = b.tc_c1 && pl->blocked_weights;
         if (b.tc_c1) SINDDM_TRY(tc_conv_prepare(c1, &b.c1));
 
         // ---- conv2: a1 -> o, + residual; l4 also carries the final 1x1 conv
@@ -230,6 +246,7 @@ int plan_build(Plan* pl, int B, int H, int W, int dim, int channels, int math, i
         if (res_c3) c2.ep.x3 = b.in;
         if (!b.has_res) c2.ep.res_add = b.in;
         c2.ep.out = (l < 3 || tr) ? b.o : nullptr;
+        c2.w_blocked = b.tc_c2 && pl->blocked_weights;
         if (b.tc_c2) SINDDM_TRY(tc_conv_prepare(c2, &b.c2));
 
         if (tr) {
@@ -289,6 +306,9 @@ int plan_build(Plan* pl, int B, int H, int W, int dim, int channels, int math, i
             b.pdr.in = d_o;
             b.pw2.dy = d_o;
             b.pwr.dy = d_o;
+            b.pd2.w_blocked = b.tc_d2 && pl->blocked_weights;
+            b.pd1.w_blocked = b.tc_d1 && pl->blocked_weights;
+            b.pdr.w_blocked = b.tc_dr && pl->blocked_weights;
             if (b.tc_d2) SINDDM_TRY(tc_conv_prepare(b.pd2, &b.d2));
             if (b.tc_d1) SINDDM_TRY(tc_conv_prepare(b.pd1, &b.d1));
             if (b.tc_dr) SINDDM_TRY(tc_conv_prepare(b.pdr, &b.dr));
@@ -322,12 +342,15 @@ int net_pack_weights(Plan* pl, const float* const* params, cudaStream_t s) {
     const int rnd = pl->math == MATH_TF32 ? 1 : 0;
     for (int l = 0; l < kNumBlocks; ++l) {
         BlockBufs& b = pl->blk[l];
-        SINDDM_TRY(pack_conv_weights_launch(params[b.pbase + 6], b.Co, b.Ci, 9, b.w0_f, b.w0_d, rnd && b.tc_c1, s));
-        SINDDM_TRY(pack_conv_weights_launch(params[b.pbase + 8], b.Co, b.Co, 9, b.w2_f, b.w2_d, rnd && b.tc_c2, s));
+        // tensor-core layers read the blocked pre-swizzled layout, CUDA-core layers the plain [tap][N][K] one
+        SINDDM_TRY(pack_conv_weights_launch(params[b.pbase + 6], b.Co, b.Ci, 9, b.w0_f, b.w0_d, rnd && b.tc_c1, s,
+                                            b.tc_c1 && pl->blocked_weights));
+        SINDDM_TRY(pack_conv_weights_launch(params[b.pbase + 8], b.Co, b.Co, 9, b.w2_f, b.w2_d, rnd && b.tc_c2, s,
+                                            b.tc_c2 && pl->blocked_weights));
         if (b.has_res) {
             if (b.Ci >= 8)
                 SINDDM_TRY(pack_conv_weights_launch(params[b.pbase + 10], b.Co, b.Ci, 1, b.wr_f, b.wr_d,
-                                                    rnd && b.tc_c2, s));
+                                                    rnd && b.tc_c2, s, b.tc_c2 && pl->blocked_weights));
             // net[2].bias + res_conv.bias enter the same epilogue
             add_vec_kernel<<<ceil_div(b.Co, 128), 128, 0, s>>>(params[b.pbase + 9], params[b.pbase + 11], b.bias2c,
                                                               b.Co);

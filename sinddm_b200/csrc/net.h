@@ -71,6 +71,7 @@ struct BlockBufs {
 struct Plan {
     int B, H, W, dim, half, channels;
     int math, training;
+    int blocked_weights;   // tensor-core layers use the blocked pre-swizzled weight layout (1-D bulk copies)
     long long P;
     float* ws;
     size_t ws_bytes;

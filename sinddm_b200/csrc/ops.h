@@ -42,6 +42,10 @@ struct ConvProblem {
     int Cres;
     const float* w_res;   // [N][Cres]
     int N;
+    // w_blocked != 0: `w` / `w_res` are in the tensor-core staging layout [tap][chunk][N][32] with the 128-byte
+    // rows pre-swizzled (pack_conv_weights_launch(..., blocked=1)); every (tap, 32-channel chunk) weight box is
+    // then one contiguous N x 128 B block that a single 1-D bulk copy brings into shared memory.
+    int w_blocked;
     ConvEpilogue ep;
 };
 
@@ -98,7 +102,9 @@ int wgrad_reduce_launch(const float* partial, int nsplit, int ntaps, int Cx, int
 //   dgrad: dst[tap][ci][co] = w[co][ci][ntaps-1-tap]
 // ------------------------------------------------------------------------------------------------
 int pack_conv_weights_launch(const float* w, int Cout, int Cin, int ntaps, float* dst_fwd, float* dst_dgrad, int round,
-                             cudaStream_t stream);
+                             cudaStream_t stream, int blocked = 0);
+// floats needed by a packed weight buffer in either layout ([ntaps][N][K] or blocked with K padded to 32)
+inline size_t packed_weight_floats(int ntaps, int N, int K) { return (size_t)ntaps * N * ((K + 31) / 32 * 32); }
 
 // ------------------------------------------------------------------------------------------------
 // Depthwise 5x5 (pad 2):  out[p][c] = add[p][c] + bias[c] + cond[b][c] + sum_tap w[c][tap(') ] * in[p (+) tap][c]

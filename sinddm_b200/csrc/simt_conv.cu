@@ -198,8 +198,19 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int nspli
     }
 }
 
+// blocked = 0: dst[tap][n][k];  blocked = 1: dst[tap][k/32][n][32] with 16-byte groups XOR-swizzled by (n & 7),
+// i.e. exactly the shared-memory image of a 128B-swizzled K-major UMMA operand tile (padding pre-zeroed).
+__device__ __forceinline__ size_t packed_index(int tap, int n, int k, int N, int K, int blocked) {
+    if (!blocked) return ((size_t)tap * N + n) * K + k;
+    const int nchunk = (K + 31) >> 5;
+    const int chunk = k >> 5, kk = k & 31;
+    const int grp = (kk >> 2) ^ (n & 7);
+    return (((size_t)tap * nchunk + chunk) * N + n) * 32 + grp * 4 + (kk & 3);
+}
+
 __global__ void pack_conv_weights_kernel(const float* __restrict__ w, int Cout, int Cin, int ntaps,
-                                         float* __restrict__ dst_fwd, float* __restrict__ dst_dgrad, int round) {
+                                         float* __restrict__ dst_fwd, float* __restrict__ dst_dgrad, int round,
+                                         int blocked) {
     const int total = Cout * Cin * ntaps;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
@@ -208,8 +219,8 @@ __global__ void pack_conv_weights_kernel(const float* __restrict__ w, int Cout, 
     const int co = i / (ntaps * Cin);
     float v = w[i];
     if (round) v = round_tf32(v);
-    if (dst_fwd) dst_fwd[((size_t)tap * Cout + co) * Cin + ci] = v;
-    if (dst_dgrad) dst_dgrad[((size_t)(ntaps - 1 - tap) * Cin + ci) * Cout + co] = v;
+    if (dst_fwd) dst_fwd[packed_index(tap, co, ci, Cout, Cin, blocked)] = v;
+    if (dst_dgrad) dst_dgrad[packed_index(ntaps - 1 - tap, ci, co, Cin, Cout, blocked)] = v;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -506,9 +517,10 @@ int wgrad_reduce_launch(const float* partial, int nsplit, int ntaps, int Cx, int
 }
 
 int pack_conv_weights_launch(const float* w, int Cout, int Cin, int ntaps, float* dst_fwd, float* dst_dgrad, int round,
-                             cudaStream_t stream) {
+                             cudaStream_t stream, int blocked) {
     const int total = Cout * Cin * ntaps;
-    pack_conv_weights_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(w, Cout, Cin, ntaps, dst_fwd, dst_dgrad, round);
+    pack_conv_weights_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(w, Cout, Cin, ntaps, dst_fwd, dst_dgrad, round,
+                                                                       blocked);
     SINDDM_CUDA_OK(cudaGetLastError());
     return SINDDM_OK;
 }

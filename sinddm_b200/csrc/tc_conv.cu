@@ -60,6 +60,8 @@ struct KernelArgs {
     int tiles_w, tiles_h, ntiles;
     int nstages_b, bbox_bytes; // weight ring: slots and bytes per slot (N x 128 B rounded up to 1 KiB)
     int slot_stride;           // TMEM columns between accumulator slots
+    const float* w_blk;        // non-null: weights in the blocked pre-swizzled layout [tap][chunk][N][32] ...
+    const float* wres_blk;     // ... (and the residual 1x1 weights [chunk][N][32]): boxes come by 1-D bulk copy
     uint32_t idesc;
     ConvEpilogue ep;
 };
@@ -102,10 +104,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     // ---------------------------------------------------------------- one-time setup
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_a);
-        tma_prefetch_desc(&tm_b);
+        if (!a.w_blk) tma_prefetch_desc(&tm_b);
         if (a.nchunks_res > 0) {
             tma_prefetch_desc(&tm_ares);
-            tma_prefetch_desc(&tm_bres);
+            if (!a.w_blk) tma_prefetch_desc(&tm_bres);
         }
         for (int i = 0; i < kStagesA; ++i) {
             mbar_init(&fulla_bar[i], TWO ? 2 : 1);   // one arrival per producing CTA
@@ -194,8 +196,15 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                     mbar_wait(&emptyb_bar[sb_i], phb ^ 1u);
                     if (!TWO) {
                         mbar_arrive_expect_tx_w(&fullb_bar[sb_i], nbytes);
-                        tma_load_2d_w(smem_b + (size_t)sb_i * a.bbox_bytes, main ? &tm_b : &tm_bres, &fullb_bar[sb_i],
-                                      c * kKC, tap * N);
+                        if (a.w_blk) {
+                            // the whole (tap, chunk) weight box is one contiguous pre-swizzled block
+                            const float* src = main ? a.w_blk + ((size_t)tap * a.nchunks + c) * N * kKC
+                                                    : a.wres_blk + (size_t)c * N * kKC;
+                            bulk_copy_g2s_w(smem_b + (size_t)sb_i * a.bbox_bytes, src, nbytes, &fullb_bar[sb_i]);
+                        } else {
+                            tma_load_2d_w(smem_b + (size_t)sb_i * a.bbox_bytes, main ? &tm_b : &tm_bres,
+                                          &fullb_bar[sb_i], c * kKC, tap * N);
+                        }
                     } else {
                         // this CTA stages rows [crank*N/2, (crank+1)*N/2) of the tap's weight matrix
                         if (crank == 0) mbar_arrive_expect_tx_w(&fullb_bar[sb_i], 2 * nbytes);
@@ -465,7 +474,7 @@ static int two_sm_setting() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("SINDDM_TC_2SM");
-        v = e ? (atoi(e) != 0) : 1;
+        v = e ? (atoi(e) != 0) : 0;   // CTA pairs are correct but currently slower: off by default
     }
     return v;
 }
@@ -484,14 +493,16 @@ int tc_conv_prepare(const ConvProblem& p, TcConvOp* op) {
     SINDDM_REQUIRE(device_info().initialized, "sinddm_init() has not been called");
     op->p = p;
     // CTA pairs (SINDDM_TC_2SM=0 disables): each CTA stages N/2 weight rows, which must be whole 8-row atoms
-    op->cs = (two_sm_setting() && p.N % 16 == 0) ? 2 : 1;
+    op->cs = (two_sm_setting() && p.N % 16 == 0 && !p.w_blocked) ? 2 : 1;
     const int cs = op->cs;
     SINDDM_TRY(make_tmap_nhwc(&op->tm_a, p.in, p.B, p.H, p.W, p.Cin, kKC, kTileW, kBoxH, CU_TENSOR_MAP_SWIZZLE_128B));
-    SINDDM_TRY(make_tmap_2d(&op->tm_b, p.w, p.Cin, p.ntaps * p.N, kKC, p.N / cs, CU_TENSOR_MAP_SWIZZLE_128B));
+    if (p.w_blocked) memset(&op->tm_b, 0, sizeof(op->tm_b));
+    else SINDDM_TRY(make_tmap_2d(&op->tm_b, p.w, p.Cin, p.ntaps * p.N, kKC, p.N / cs, CU_TENSOR_MAP_SWIZZLE_128B));
     if (p.in_res) {
         SINDDM_TRY(make_tmap_nhwc(&op->tm_ares, p.in_res, p.B, p.H, p.W, p.Cres, kKC, kTileW, kBoxH,
                                   CU_TENSOR_MAP_SWIZZLE_128B));
-        SINDDM_TRY(make_tmap_2d(&op->tm_bres, p.w_res, p.Cres, p.N, kKC, p.N / cs, CU_TENSOR_MAP_SWIZZLE_128B));
+        if (p.w_blocked) memset(&op->tm_bres, 0, sizeof(op->tm_bres));
+        else SINDDM_TRY(make_tmap_2d(&op->tm_bres, p.w_res, p.Cres, p.N, kKC, p.N / cs, CU_TENSOR_MAP_SWIZZLE_128B));
     } else {
         op->tm_ares = op->tm_a;
         op->tm_bres = op->tm_b;
@@ -541,6 +552,8 @@ int tc_conv_launch(const TcConvOp& op, cudaStream_t stream) {
     a.bbox_bytes = op.stage_bytes;
     a.slot_stride = (int)align_up((size_t)p.N, 32);
     a.idesc = umma_idesc_tf32(op.cs == 2 ? 256 : 128, p.N, 0, 0);
+    a.w_blk = p.w_blocked ? p.w : nullptr;
+    a.wres_blk = p.w_blocked ? p.w_res : nullptr;
     a.ep = p.ep;
     // algorithmic work: real pixels x N x (taps*Cin + Cres) MACs
     prof_begin(stream, 0, 2.0 * (double)p.B * p.H * p.W * p.N * ((double)p.ntaps * p.Cin + a.Cres));
