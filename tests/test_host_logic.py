@@ -113,3 +113,23 @@ def test_dataset_yields_first_image_replicated(tmp_path):
     assert orig.shape == (128, 3, 9, 11) and blur.shape == (128, 3, 9, 11)
     assert torch.equal(orig[0], torch.from_numpy(a).permute(2, 0, 1).float() / 255 * 2 - 1)
     assert torch.equal(blur[5], torch.from_numpy(b).permute(2, 0, 1).float() / 255 * 2 - 1)
+
+
+def test_cli_accepts_the_reference_flags():
+    """main.py parses every flag of the reference CLI (main.py:15-58)."""
+    import importlib.util
+    import pathlib
+    spec = importlib.util.spec_from_file_location("sinddm_main", pathlib.Path(__file__).parents[1] / "main.py")
+    cli = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cli)
+    args = cli.build_parser().parse_args(
+        "--scope balloons --mode train --input_image a.png --start_t_harm 5 --start_t_style 15 --harm_mask m.png "
+        "--clip_text hello --fill_factor 0.5 --strength 0.3 --roi_n_tar 2 --dataset_folder ./d/ --image_name b.png "
+        "--results_folder ./r/ --dim 160 --scale_factor 1.411 --timesteps 100 --train_batch_size 32 "
+        "--grad_accumulate 1 --train_num_steps 120001 --save_and_sample_every 10000 --avg_window 100 "
+        "--train_lr 0.001 --sched_k_milestones 20 40 70 80 90 110 --load_milestone 0 --sample_batch_size 16 "
+        "--scale_mul 1 1 --sample_t_list 52 41 31 22 --device_num 0 --sample_limited_t --omega 0 "
+        "--loss_factor 1".split())
+    assert args.sched_k_milestones == [20, 40, 70, 80, 90, 110] and args.scale_mul == [1.0, 1.0]
+    with pytest.raises(SystemExit):
+        cli.main(["--mode", "clip_content"])
