@@ -415,23 +415,36 @@ __global__ void simt_wgrad_smallcx_kernel(const WgradProblem p) {
     float acc[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) acc[k] = 0.f;
-    for (long long q = p_begin + py; q < p_end; q += kPY) {
+    // 4 pixels per iteration: their dy / x loads are independent and issue back to back (the per-pixel loop was
+    // bound by one L2 round trip per iteration)
+    constexpr int U = 4;
+    for (long long q0 = p_begin + py; q0 < p_end; q0 += (long long)kPY * U) {
         if (!act) continue;
-        const int w = (int)(q % p.W);
-        const int h = (int)((q / p.W) % p.H);
-        const float g = __ldg(p.dy + q * p.Cy + co);
+        float g[U];
 #pragma unroll
-        for (int tap = 0; tap < NTAPS; ++tap) {
-            int dyo = 0, dxo = 0;
-            if (NTAPS == 9) {
-                dyo = tap / 3 - 1;
-                dxo = tap % 3 - 1;
+        for (int u = 0; u < U; ++u) {
+            const long long q = q0 + (long long)u * kPY;
+            g[u] = q < p_end ? __ldg(p.dy + q * p.Cy + co) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long q = q0 + (long long)u * kPY;
+            if (q >= p_end) continue;
+            const int w = (int)(q % p.W);
+            const int h = (int)((q / p.W) % p.H);
+#pragma unroll
+            for (int tap = 0; tap < NTAPS; ++tap) {
+                int dyo = 0, dxo = 0;
+                if (NTAPS == 9) {
+                    dyo = tap / 3 - 1;
+                    dxo = tap % 3 - 1;
+                }
+                const int hh = h + dyo, ww = w + dxo;
+                if (hh < 0 || hh >= p.H || ww < 0 || ww >= p.W) continue;
+                const float* xs = p.x + (q + (long long)dyo * p.W + dxo) * CX;
+#pragma unroll
+                for (int ci = 0; ci < CX; ++ci) acc[tap * CX + ci] = fmaf(__ldg(xs + ci), g[u], acc[tap * CX + ci]);
             }
-            const int hh = h + dyo, ww = w + dxo;
-            if (hh < 0 || hh >= p.H || ww < 0 || ww >= p.W) continue;
-            const float* xs = p.x + (q + (long long)dyo * p.W + dxo) * CX;
-#pragma unroll
-            for (int ci = 0; ci < CX; ++ci) acc[tap * CX + ci] = fmaf(__ldg(xs + ci), g, acc[tap * CX + ci]);
         }
     }
 #pragma unroll
