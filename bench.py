@@ -63,13 +63,14 @@ class ClockSampler(threading.Thread):
             self.sm_max = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
             names = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
                      0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown"}
-            while not self.stop_flag.is_set():
+            while True:
                 self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
                 bits = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
                 for bit, name in names.items():
                     if bits & bit:
                         self.reasons.add(name)
-                time.sleep(0.1)
+                if self.stop_flag.wait(0.05):       # at least one sample is always taken
+                    break
         except Exception as e:  # NVML missing: report nulls rather than fail the bench
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
 
@@ -318,6 +319,9 @@ def run_b200_arm(args):
     sample_e2e_s = reduce_max(time.perf_counter() - t0)
     finite = bool(torch.isfinite(host_imgs).all())
 
+    if world > 1:
+        tdist.barrier()
+        tdist.destroy_process_group()
     if rank != 0:
         return
     peaks = {}

@@ -265,89 +265,9 @@ dw5x5_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const float* __restr
     });
 }
 
-// Two channels per thread (64-channel boxes): the kernel above is instruction-issue bound (IPC 3.1 of 4,
-// profiles/), so this variant halves the instruction count per channel with 64-bit shared loads and packed
-// fp32x2 FMAs (FFMA2).  Used for wide layers (C >= 128).
-constexpr int kTileFloats2 = kTileRows * kTileCols * 64;  // 110592 B
-
-__global__ void __launch_bounds__(256, 2)
-dw5x5_tma2_kernel(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ wgt,
-                  const float* __restrict__ bias, const float* __restrict__ cond, const float* __restrict__ add,
-                  float* __restrict__ out, int H, int W, int C, int tiles_w, int flip, int round) {
-    extern __shared__ __align__(128) uint8_t dsm[];
-    const float2* tile = reinterpret_cast<const float2*>(dsm);   // [rows][cols][32 lanes] of channel pairs
-    uint64_t* bar = reinterpret_cast<uint64_t*>(dsm + kTileFloats2 * sizeof(float));
-    const int lane = threadIdx.x, ry = threadIdx.y;
-    const int tw = blockIdx.x % tiles_w;
-    const int cg = blockIdx.x / tiles_w;
-    const int th = blockIdx.y, b = blockIdx.z;
-    const int tid = ry * 32 + lane;
-    if (tid == 0) {
-        mbar_init(bar, 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-    if (tid == 0) {
-        mbar_arrive_expect_tx(bar, kTileFloats2 * sizeof(float));
-        tma_load_4d(dsm, &tm_in, bar, cg * 64, tw * kTW - 2, th * kTH - 2, b);
-    }
-    const int c = cg * 64 + 2 * lane;
-    const int h = th * kTH + ry;
-    const bool cok = c < C;   // C is even: both channels of the pair are valid together
-    float2 wr[5][5];
-#pragma unroll
-    for (int t = 0; t < 25; ++t) {
-        const int ts = flip ? 24 - t : t;
-        wr[t / 5][t % 5] = cok ? make_float2(__ldg(wgt + c * 25 + ts), __ldg(wgt + (c + 1) * 25 + ts))
-                               : make_float2(0.f, 0.f);
-    }
-    float2 bv = make_float2(0.f, 0.f), cv = make_float2(0.f, 0.f);
-    if (cok) {
-        if (bias) bv = *reinterpret_cast<const float2*>(bias + c);
-        if (cond) cv = *reinterpret_cast<const float2*>(cond + (size_t)b * C + c);
-    }
-    mbar_wait(bar, 0);
-    if (!cok || h >= H) return;
-    const size_t rowoff = (((size_t)b * H + h) * W) * C + c;
-    const int w0 = tw * kTW;
-    const float2* base = tile + (size_t)ry * kTileCols * 32 + lane;
-
-    float2 win[5][5];   // win[ky][slot], slot = tile column modulo 5
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int ky = 0; ky < 5; ++ky) win[ky][j] = base[(ky * kTileCols + j) * 32];
-    for (int wq = 0; wq < kTW; wq += 5) {
-#pragma unroll
-        for (int j = 0; j < 5; ++j) {
-            const int wo = wq + j;
-            if (wo < kTW) {
-#pragma unroll
-                for (int ky = 0; ky < 5; ++ky) win[ky][(j + 4) % 5] = base[(ky * kTileCols + wo + 4) * 32];
-                const int w = w0 + wo;
-                if (w < W) {
-                    float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-                    for (int ky = 0; ky < 5; ++ky)
-#pragma unroll
-                        for (int kx = 0; kx < 5; ++kx) acc = __ffma2_rn(win[ky][(j + kx) % 5], wr[ky][kx], acc);
-                    const size_t off = rowoff + (size_t)w * C;
-                    float2 v = make_float2((acc.x + bv.x) + cv.x, (acc.y + bv.y) + cv.y);
-                    if (add) {
-                        const float2 ad = __ldg(reinterpret_cast<const float2*>(add + off));
-                        v.x += ad.x;
-                        v.y += ad.y;
-                    }
-                    if (round) {
-                        v.x = round_tf32(v.x);
-                        v.y = round_tf32(v.y);
-                    }
-                    *reinterpret_cast<float2*>(out + off) = v;
-                }
-            }
-        }
-    }
-}
+// (A two-channels-per-thread variant with 64-channel boxes and packed fp32x2 FMAs was measured slower --
+// 1.03 ms vs 0.76 ms per 160-channel launch at 32x186x248 -- because its 125 registers halve the resident
+// warps; the one-channel kernel above stays.)
 
 // grid = (channel groups, row chunks, B); the CTA walks the column tiles of its 8-row chunk with a
 // double-buffered TMA pipeline and keeps the 26 sums per (channel, row) in registers.
@@ -432,24 +352,6 @@ dw5x5_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __
 int dw5x5_launch(const float* in, const float* w, const float* bias, const float* cond, const float* add, float* out,
                  int B, int H, int W, int C, int flip, int round_tf32, cudaStream_t stream) {
     SINDDM_REQUIRE(B <= 65535, "dw5x5: batch too large");
-    if (C % 4 == 0 && C >= 128 && device_info().initialized) {
-        CUtensorMap tm;
-        SINDDM_TRY(make_tmap_nhwc(&tm, in, B, H, W, C, 64, kTileCols, kTileRows, CU_TENSOR_MAP_SWIZZLE_NONE));
-        const int tiles_w = ceil_div(W, kTW);
-        const size_t smem = kTileFloats2 * sizeof(float) + 16;
-        static int attr_set2 = 0;
-        if (!attr_set2) {
-            SINDDM_CUDA_OK(cudaFuncSetAttribute(dw5x5_tma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                (int)smem));
-            attr_set2 = 1;
-        }
-        dim3 grid(tiles_w * ceil_div(C, 64), ceil_div(H, kTH), B);
-        dim3 block(32, kTH);
-        dw5x5_tma2_kernel<<<grid, block, smem, stream>>>(tm, w, bias, cond, add, out, H, W, C, tiles_w, flip,
-                                                         round_tf32);
-        SINDDM_CUDA_OK(cudaGetLastError());
-        return SINDDM_OK;
-    }
     if (C % 4 == 0 && device_info().initialized) {
         CUtensorMap tm;
         SINDDM_TRY(make_tmap_nhwc(&tm, in, B, H, W, C, 32, kTileCols, kTileRows, CU_TENSOR_MAP_SWIZZLE_NONE));
