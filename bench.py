@@ -289,14 +289,18 @@ def run_b200_arm(args):
         loss = trainer.train_step(s=s)
         return loss.item()                    # device -> host read of the step's result
 
-    for i in range(min(args.warmup, 5)):
+    for i in range(max(args.warmup, 5)):
         e2e_step(i)
     barrier()
+    e2e_per_scale = [0.0] * 5
     t0 = time.perf_counter()
     for i in range(args.steps):
+        ts = time.perf_counter()
         e2e_step(i)
+        e2e_per_scale[i % 5] += time.perf_counter() - ts
     barrier()
     e2e_s = reduce_max(time.perf_counter() - t0)
+    e2e_per_scale = [1e3 * v / max(1, len(range(k, args.steps, 5))) for k, v in enumerate(e2e_per_scale)]
 
     # ---- sampling: sample_scales, 16 images per GPU ----------------------------------------------------
     def sample_once():
@@ -363,6 +367,7 @@ def run_b200_arm(args):
                 "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
         "per_scale_ms_per_step": per_scale,
+        "e2e_per_scale_ms_per_step": e2e_per_scale,
         "finest_scale_steps_per_sec": 1e3 / per_scale[4] * world,
         "achieved_tflops_whole_step": TRAIN_FLOP_PER_PX * mean_px() * BATCH * steps_per_s / 1e12,
         "roofline": {"bound": "tensor", "kernel": "tc_conv_kernel (3x3/1x1 conv forward + data gradient)",

@@ -72,7 +72,7 @@ class MultiscaleTrainer(object):
                  image_sizes=None, train_batch_size=32, train_lr=2e-5, train_num_steps=100000,
                  gradient_accumulate_every=2, fp16=False, step_start_ema=2000, update_ema_every=10,
                  save_and_sample_every=25000, avg_window=100, sched_milestones=None, results_folder='./results',
-                 device=None):
+                 device=None, scale_draw='device'):
         super().__init__()
         self.device = device
         self.sched_milestones = [10000, 30000, 60000, 80000, 90000] if sched_milestones is None else sched_milestones
@@ -85,6 +85,10 @@ class MultiscaleTrainer(object):
         self.save_and_sample_every = save_and_sample_every
         self.avg_window = avg_window
 
+        # 'device': torch.multinomial on the device like the reference (trainer.py:197; same RNG stream, but the
+        # call costs ~6.6 ms of host time per step on a B200 box, profiles/); 'host': the same uniform draw from a
+        # CPU generator (microseconds; the device stream of t / noise then differs from the reference's)
+        self.scale_draw = scale_draw
         self.batch_size = train_batch_size           # GLOBAL batch (split over ranks under torchrun)
         self.n_scales = n_scales
         self.scale_factor = scale_factor
@@ -178,7 +182,10 @@ class MultiscaleTrainer(object):
     def train_step(self, s=None):
         """One optimizer step (trainer.py:196-214).  Returns the (device, fp32) loss of the last micro-batch."""
         if s is None:
-            s = torch.multinomial(input=self._s_weights, num_samples=1)
+            if self.scale_draw == 'host':
+                s = torch.multinomial(input=self._s_weights_host, num_samples=1, generator=self._host_gen)
+            else:
+                s = torch.multinomial(input=self._s_weights, num_samples=1)
         s = int(s)                                        # the reference syncs here too (list index by tensor)
         loss = None
         for _ in range(self.gradient_accumulate_every):
@@ -208,6 +215,9 @@ class MultiscaleTrainer(object):
 
     def _prepare_training(self):
         self._s_weights = torch.tensor(self.model.num_timesteps_trained, device=self.device, dtype=torch.float)
+        self._s_weights_host = self._s_weights.cpu()
+        if not hasattr(self, '_host_gen'):
+            self._host_gen = torch.Generator().manual_seed(torch.initial_seed() % (2 ** 63))
         if not hasattr(self, '_loss_acc'):
             self._loss_acc = torch.zeros((), dtype=torch.float64, device=self.device)
 
