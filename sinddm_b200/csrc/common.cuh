@@ -164,6 +164,21 @@ SINDDM_DEVINL void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t*
         : "memory");
 }
 
+// Tile store shared -> global (elements outside the tensor are clipped).  Completion is tracked per issuing
+// thread in bulk async-groups: commit after the store, wait_group_read<N> before the staging buffer of all but
+// the N most recent groups is overwritten.  The smem writes being stored need fence_proxy_async_smem() first.
+SINDDM_DEVINL void tma_store_4d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+SINDDM_DEVINL void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+SINDDM_DEVINL void bulk_wait_group_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
 // Whole-warp ("_w") versions: executed by all 32 lanes of a converged warp, the lane election happens inside
 // the asm by predication, so the surrounding loop stays in uniform control flow (see elect_one_sync()).
 SINDDM_DEVINL void mbar_arrive_expect_tx_w(uint64_t* bar, uint32_t bytes) {

@@ -52,6 +52,7 @@ struct ConvProblem {
 // tcgen05 path: needs Cin % 8 == 0, Cres % 8 == 0, N % 16 == 0, 16 <= N <= 160.
 struct TcConvOp {
     CUtensorMap tm_a, tm_ares, tm_b, tm_bres;
+    CUtensorMap tm_out, tm_pre, tm_in;   // epilogue: result / pre-activation stores, streamed-operand loads
     ConvProblem p;
     int stage_bytes, nstages, smem_bytes;
     int tiles_w, tiles_h, ntiles, grid;

@@ -23,9 +23,9 @@
 //   * operands land in 128B-swizzled K-major tiles that the UMMA descriptors consume directly.
 //   accumulators   fp32 in TMEM: three slots of N columns; tile pair p uses slots (2p, 2p+1) mod 3, so the
 //                  main loop of pair p+1 only waits for the epilogue of the FIRST half of pair p.
-//   roles          warp 0: TMA producer | warp 1: TMEM alloc + MMA issue (whole warps in uniform control flow,
+//   roles          (warpgroup aligned) warp 0: TMA producer | warp 1: TMEM alloc + MMA issue (whole warps in uniform control flow,
 //                  the issuing lane is elected inside the asm: this removed a ~250-cycle/MMA issue cost)
-//                  warps 2-9: epilogue (TMEM -> registers -> bias/residual/GELU/... -> global), two warps per
+//                  warps 4-11: epilogue (TMEM -> registers -> bias/residual/GELU/... -> global), two warps per
 //                  TMEM lane quarter splitting the columns, global operands prefetched one chunk ahead
 //   grid           persistent, min(#tiles, #SMs) CTAs, static round-robin over tiles.
 #include <stdlib.h>
@@ -45,12 +45,19 @@ constexpr int kKC = 32;                      // channels per K chunk (32 fp32 = 
 constexpr int kRowBytes = kTileW * kKC * 4;  // one image row of the box: 16 px x 128 B = 2 KiB
 constexpr int kABytes = kBoxH * kRowBytes;   // 36 KiB
 constexpr int kMaxN = 160;
-constexpr int kThreads = 320;       // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr int kThreads = 384;       // warp 0 TMA, warp 1 MMA, (warps 2-3 idle), warps 4-11 epilogue
+constexpr int kEpiWarp0 = 4;        // roles are warpgroup aligned so that setmaxnreg can move registers between them
 constexpr int kEpiThreads = 256;
 constexpr int kTmemCols = 512;
 constexpr int kSlots = 3;
 constexpr int kStagesA = 3;   // activation (halo box) ring
 constexpr int kMaxStagesB = 8;   // weight box ring
+// epilogue staging: every epilogue warp owns three [32 px][16 ch] tiles (64B-swizzled, 2 KiB): one filled by a TMA
+// load of the streamed operand (residual / pre-activation), two drained by TMA stores of the results
+constexpr int kEpiChunk = 16;
+constexpr int kEpiTileBytes = 32 * kEpiChunk * 4;
+constexpr int kEpiWarpBytes = 3 * kEpiTileBytes;
+constexpr int kEpiBytes = (kEpiThreads / 32) * kEpiWarpBytes;   // 48 KiB
 
 struct KernelArgs {
     int B, H, W;
@@ -63,14 +70,15 @@ struct KernelArgs {
     const float* w_blk;        // non-null: weights in the blocked pre-swizzled layout [tap][chunk][N][32] ...
     const float* wres_blk;     // ... (and the residual 1x1 weights [chunk][N][32]): boxes come by 1-D bulk copy
     uint32_t idesc;
+    int dbg;                   // diagnostics (SINDDM_TC_DEBUG): 1 = no operand loads, 2 = no epilogue traffic, 4 = no MMAs
     ConvEpilogue ep;
 };
 
 // smem tail (after the 1024-aligned stage ring):
-//   uint64 fullA[3], emptyA[3], fullB[8], emptyB[8], tfull[3], tempty[3]; uint32 tmem_slot[4];
+//   uint64 fullA[3], emptyA[3], fullB[8], emptyB[8], tfull[3], tempty[3], epi_in[8]; uint32 tmem_slot[4];
 //   float bias[kMaxN], wres3[kMaxN*3], wfinal[3*kMaxN], bfinal[4]
-constexpr int kTailBytes =
-    (2 * kStagesA + 2 * kMaxStagesB + 2 * kSlots) * 8 + 16 + (kMaxN + kMaxN * 3 + 3 * kMaxN + 4 + 128 * 3) * 4 + 64;
+constexpr int kTailBytes = (2 * kStagesA + 2 * kMaxStagesB + 2 * kSlots + kEpiThreads / 32) * 8 + 16 +
+                           (kMaxN + kMaxN * 3 + 3 * kMaxN + 4 + 128 * 3) * 4 + 64;
 
 // TWO = true: CTA pairs (cluster of 2, cta_group::2): one M=256 MMA covers the same half of BOTH CTAs' tiles,
 // each CTA stages only half of the weight rows, and only the leader CTA issues MMAs.
@@ -78,19 +86,22 @@ template <bool TWO>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_ares,
                const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_bres,
-               const KernelArgs a) {
+               const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_pre,
+               const __grid_constant__ CUtensorMap tm_in, const KernelArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
     uint8_t* smem_b = smem + (size_t)kStagesA * kABytes;
-    uint8_t* tail = smem_b + (size_t)a.nstages_b * a.bbox_bytes;
+    uint8_t* smem_epi = smem_b + (size_t)a.nstages_b * a.bbox_bytes;
+    uint8_t* tail = smem_epi + kEpiBytes;
     uint64_t* fulla_bar = reinterpret_cast<uint64_t*>(tail);
     uint64_t* emptya_bar = fulla_bar + kStagesA;
     uint64_t* fullb_bar = emptya_bar + kStagesA;
     uint64_t* emptyb_bar = fullb_bar + kMaxStagesB;
     uint64_t* tfull_bar = emptyb_bar + kMaxStagesB;
     uint64_t* tempty_bar = tfull_bar + kSlots;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + kSlots);
+    uint64_t* epi_in_bar = tempty_bar + kSlots;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_in_bar + kEpiThreads / 32);
     float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
     float* s_wres3 = s_bias + kMaxN;
     float* s_wfinal = s_wres3 + kMaxN * 3;
@@ -121,14 +132,15 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             mbar_init(&tfull_bar[i], 1);
             mbar_init(&tempty_bar[i], (TWO ? 2 : 1) * (kEpiThreads / 32));   // one arrival per epilogue warp
         }
+        for (int i = 0; i < kEpiThreads / 32; ++i) mbar_init(&epi_in_bar[i], 1);
         fence_mbar_init();
     }
     if (warp == 1) {
         if (TWO) tmem_alloc_2sm(tmem_slot, kTmemCols);
         else tmem_alloc(tmem_slot, kTmemCols);
     }
-    if (warp >= 2) {
-        const int t = threadIdx.x - 64;
+    if (warp >= kEpiWarp0) {
+        const int t = threadIdx.x - kEpiWarp0 * 32;
         for (int i = t; i < N; i += kEpiThreads) s_bias[i] = a.ep.bias ? a.ep.bias[i] : 0.f;
         if (a.ep.w_res3)
             for (int i = t; i < N * 3; i += kEpiThreads) s_wres3[i] = a.ep.w_res3[i];
@@ -156,7 +168,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 
     // Roles 0 and 1 run their loops with ALL 32 lanes (uniform control flow); TMA, MMA and commit instructions
     // elect their single issuing lane inside the asm (common.cuh) -- see elect_one_sync() for why.
-    if (warp == 0) {
+    // the launch gives every thread 168 registers; the producer / MMA warpgroup hands most of its share to the
+    // epilogue warpgroups, which keep a whole half tile's accumulator columns in registers (384*168 = 128*56 + 256*224)
+    if (warp < kEpiWarp0) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 72;" ::: "memory");
+      if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
         int sa_i = 0, sb_i = 0;
         uint32_t pha = 0, phb = 0;
@@ -174,7 +190,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                 const int kx = main ? it - c * nkx : 0;
                 // activation halo box: rows h0-1 .. h0+16, columns shifted by the horizontal tap
                 mbar_wait(&emptya_bar[sa_i], pha ^ 1u);
-                if (!TWO) {
+                if (!TWO && (a.dbg & 1)) {
+                    mbar_arrive_expect_tx_w(&fulla_bar[sa_i], 0);
+                } else if (!TWO) {
                     mbar_arrive_expect_tx_w(&fulla_bar[sa_i], kABytes);
                     tma_load_4d_w(smem + (size_t)sa_i * kABytes, main ? &tm_a : &tm_ares, &fulla_bar[sa_i], c * kKC,
                                   w0 + ((main && nkx == 3) ? kx - 1 : 0), h0 - 1, b);
@@ -194,7 +212,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                 for (int ky = 0; ky < kys; ++ky) {
                     const int tap = (main && nkx == 3) ? ky * 3 + kx : 0;
                     mbar_wait(&emptyb_bar[sb_i], phb ^ 1u);
-                    if (!TWO) {
+                    if (!TWO && (a.dbg & 1)) {
+                        mbar_arrive_expect_tx_w(&fullb_bar[sb_i], 0);
+                    } else if (!TWO) {
                         mbar_arrive_expect_tx_w(&fullb_bar[sb_i], nbytes);
                         if (a.w_blk) {
                             // the whole (tap, chunk) weight box is one contiguous pre-swizzled block
@@ -219,7 +239,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                 }
             }
         }
-    } else if (warp == 1 && crank == 0) {
+      } else if (warp == 1 && crank == 0) {
         // ------------------------------------------------------------ MMA issuer (leader CTA of a pair)
         int sa_i = 0, sb_i = 0;
         uint32_t pha = 0, phb = 0;
@@ -264,8 +284,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                         umma_tf32_ss_x4_2sm(d1, a1, bb, desc_hi, 2u, a.idesc, acc, nmma);
                         umma_commit_2sm_elect(&emptyb_bar[sb_i]);
                     } else {
-                        umma_tf32_ss_x4(d0, a0, bb, desc_hi, 2u, a.idesc, acc, nmma);
-                        umma_tf32_ss_x4(d1, a1, bb, desc_hi, 2u, a.idesc, acc, nmma);
+                        if (!(a.dbg & 4)) {
+                            umma_tf32_ss_x4(d0, a0, bb, desc_hi, 2u, a.idesc, acc, nmma);
+                            umma_tf32_ss_x4(d1, a1, bb, desc_hi, 2u, a.idesc, acc, nmma);
+                        }
                         umma_commit_elect(&emptyb_bar[sb_i]);
                     }
                     if (++sb_i == a.nstages_b) {
@@ -288,15 +310,31 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                 umma_commit_elect(&tfull_bar[s1]);
             }
         }
-    } else if (warp >= 2) {
+      }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 216;" ::: "memory");
         // ------------------------------------------------------------ epilogue warps (8)
-        // warp w reads TMEM lane quarter (w & 3); the two warps of a quarter split the 16-column chunks
-        // (even / odd), so a half tile is drained by 256 threads.
+        // warp w reads TMEM lane quarter (w & 3) = 32 pixels = a 16 x 2 pixel strip; the two warps of a quarter
+        // split the 16-column chunks (even / odd).  Results never touch the LSU on their way out: a lane owns one
+        // pixel, so a direct float4 store would scatter a warp instruction over 32 cache lines (the kernel used to
+        // be bound by exactly that).  Instead each warp assembles a [32 px][16 ch] tile in shared memory and one
+        // lane hands it to the TMA unit as a (16 ch, 16 w, 2 h) box store, which also clips the image border.
+        // The streamed input operand (residual or saved pre-activation) arrives the same way, one chunk ahead.
+        const int ew = warp - kEpiWarp0;
         const int quarter = warp & 3;
-        const int cgrp = (warp - 2) >> 2;         // 0: chunks 0,2,4..  1: chunks 1,3,5..
+        const int cgrp = ew >> 2;                 // 0: chunks 0,2,4..  1: chunks 1,3,5..
         const int row = quarter * 32 + lane;      // accumulator row == pixel within the half tile
         const ConvEpilogue& ep = a.ep;
         float* s_fin = reinterpret_cast<float*>(s_bfinal + 4);   // [128][3] partial final-conv sums of group 1
+        uint8_t* stg_in = smem_epi + (size_t)ew * kEpiWarpBytes;
+        uint8_t* stg_out = stg_in + kEpiTileBytes;
+        uint64_t* in_bar = &epi_in_bar[ew];
+        // 64B swizzle: the 16-byte unit index of a row is XORed with bits 7-8 of the row's byte offset
+        const uint32_t lrow = (uint32_t)lane * 64u, swz = (uint32_t)(lane >> 1) & 3u;
+        uint32_t in_phase = 0;
+        int obuf = 0;
+        const float* gsrc = ep.res_add ? ep.res_add : ep.dgelu_z;   // streamed through TMA
+        const float* gsrc2 = (ep.res_add && ep.dgelu_z) ? ep.dgelu_z : nullptr;   // rare second stream: plain loads
         uint32_t slot_uses[kSlots] = {0, 0, 0};
         int titer = 0;
         for (int st = pair_id; st < nsuper; st += npairs, ++titer) {
@@ -304,11 +342,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             const int tw = tile % a.tiles_w;
             const int th = (tile / a.tiles_w) % a.tiles_h;
             const int b = tile / (a.tiles_w * a.tiles_h);
+            const bool live = (tile < a.ntiles) && !(a.dbg & 2);
 #pragma unroll 1
             for (int half = 0; half < 2; ++half) {
                 const int slot = (2 * titer + half) % kSlots;
                 const int h = th * kTileH + half * 8 + row / kTileW, w = tw * kTileW + row % kTileW;
-                const bool valid = (tile < a.ntiles) && (h < a.H) && (w < a.W);
+                const int hq = th * kTileH + half * 8 + quarter * 2, w0 = tw * kTileW;   // this warp's strip
+                const bool valid = live && (h < a.H) && (w < a.W);
                 const size_t pix = ((size_t)b * a.H + h) * a.W + w;
 
                 float x3v[3] = {0.f, 0.f, 0.f};
@@ -319,14 +359,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                 }
                 float fin[3] = {0.f, 0.f, 0.f};
 
-                // global operands of the first chunk are requested before the accumulator is even ready
-                const float* gsrc = ep.res_add ? ep.res_add : ep.dgelu_z;   // at most one streams per layer here
-                const float* gsrc2 = (ep.res_add && ep.dgelu_z) ? ep.dgelu_z : nullptr;
-                float4 pre[4], pre2[4];
-                int cc = cgrp * 16;
-                if (gsrc && valid && cc < N) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) pre[q] = __ldg(reinterpret_cast<const float4*>(gsrc + pix * N + cc) + q);
+                // the first chunk of the streamed operand is requested before the accumulator is even ready
+                int cc = cgrp * kEpiChunk;
+                if (gsrc && live && cc < N && lane == 0) {
+                    mbar_arrive_expect_tx(in_bar, kEpiTileBytes);
+                    tma_load_4d(stg_in, &tm_in, in_bar, cc, w0, hq, b);
                 }
 
                 mbar_wait(&tfull_bar[slot], slot_uses[slot] & 1u);
@@ -334,25 +371,49 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                 tc_fence_after_sync();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(slot * a.slot_stride);
 
+                auto store_tile = [&](const CUtensorMap* map, const int cc, const float (&v)[16]) {
+                    uint8_t* buf = stg_out + obuf * kEpiTileBytes;
+                    obuf ^= 1;
+                    if (lane == 0) bulk_wait_group_read<1>();   // the store issued from this buffer two stores ago
+                    __syncwarp();
+#pragma unroll
+                    for (uint32_t q = 0; q < 4; ++q)
+                        *reinterpret_cast<float4*>(buf + lrow + ((q ^ swz) << 4)) =
+                            make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_4d(map, buf, cc, w0, hq, b);
+                        bulk_commit_group();
+                    }
+                };
+
                 // TMEM -> register loads are double buffered: chunk i+1 is in flight while chunk i is processed
                 auto process = [&](const int cc, const uint32_t (&raw)[16]) {
                     float v[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
-                    float4 cur[4];
+                    float4 cur[4], pre2[4];
+                    if (gsrc && live) {
+                        mbar_wait(in_bar, in_phase);
+                        in_phase ^= 1u;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) cur[q] = pre[q];
-                    const size_t off = pix * N + cc;
-                    if (valid) {
-                        if (gsrc && cc + 32 < N) {   // prefetch the next chunk of this warp
-#pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                pre[q] = __ldg(reinterpret_cast<const float4*>(gsrc + off + 32) + q);
+                        for (uint32_t q = 0; q < 4; ++q)
+                            cur[q] = *reinterpret_cast<const float4*>(stg_in + lrow + ((q ^ swz) << 4));
+                        __syncwarp();
+                        if (lane == 0 && cc + 2 * kEpiChunk < N) {   // next chunk of this warp
+                            mbar_arrive_expect_tx(in_bar, kEpiTileBytes);
+                            tma_load_4d(stg_in, &tm_in, in_bar, cc + 2 * kEpiChunk, w0, hq, b);
                         }
-                        if (gsrc2) {
+                    } else {
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) pre2[q] = __ldg(reinterpret_cast<const float4*>(gsrc2 + off) + q);
-                        }
+                        for (int q = 0; q < 4; ++q) cur[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    if (gsrc2) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            pre2[q] = valid ? __ldg(reinterpret_cast<const float4*>(gsrc2 + pix * N + cc) + q)
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] += s_bias[cc + j];
@@ -363,77 +424,66 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                             v[j] = fmaf(x3v[2], wr[2], fmaf(x3v[1], wr[1], fmaf(x3v[0], wr[0], v[j])));
                         }
                     }
-                    if (valid) {
-                        if (ep.res_add) {
+                    if (ep.res_add) {
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                v[4 * q + 0] += cur[q].x;
-                                v[4 * q + 1] += cur[q].y;
-                                v[4 * q + 2] += cur[q].z;
-                                v[4 * q + 3] += cur[q].w;
-                            }
+                        for (int q = 0; q < 4; ++q) {
+                            v[4 * q + 0] += cur[q].x;
+                            v[4 * q + 1] += cur[q].y;
+                            v[4 * q + 2] += cur[q].z;
+                            v[4 * q + 3] += cur[q].w;
                         }
-                        if (ep.out_pre) {
-                            float4* o4 = reinterpret_cast<float4*>(ep.out_pre + off);
+                    }
+                    if (ep.out_pre && live) store_tile(&tm_pre, cc, v);
+                    if (ep.gelu) {
 #pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                o4[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                        for (int j = 0; j < 16; ++j) v[j] = gelu_fast(v[j]);
+                    }
+                    if (ep.dgelu_z) {
+                        const float4* z = gsrc2 ? pre2 : cur;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            v[4 * q + 0] *= gelu_grad_fast(z[q].x);
+                            v[4 * q + 1] *= gelu_grad_fast(z[q].y);
+                            v[4 * q + 2] *= gelu_grad_fast(z[q].z);
+                            v[4 * q + 3] *= gelu_grad_fast(z[q].w);
                         }
-                        if (ep.gelu) {
+                    }
+                    if (ep.w_final) {
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) v[j] = gelu_fast(v[j]);
+                        for (int j = 0; j < 16; ++j) {
+                            fin[0] = fmaf(v[j], s_wfinal[0 * N + cc + j], fin[0]);
+                            fin[1] = fmaf(v[j], s_wfinal[1 * N + cc + j], fin[1]);
+                            fin[2] = fmaf(v[j], s_wfinal[2 * N + cc + j], fin[2]);
                         }
-                        if (ep.dgelu_z) {
-                            const float4* z = gsrc2 ? pre2 : cur;
+                    }
+                    if (ep.out && live) {
+                        if (ep.round_tf32) {
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                v[4 * q + 0] *= gelu_grad_fast(z[q].x);
-                                v[4 * q + 1] *= gelu_grad_fast(z[q].y);
-                                v[4 * q + 2] *= gelu_grad_fast(z[q].z);
-                                v[4 * q + 3] *= gelu_grad_fast(z[q].w);
-                            }
+                            for (int j = 0; j < 16; ++j) v[j] = round_tf32(v[j]);
                         }
-                        if (ep.w_final) {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                fin[0] = fmaf(v[j], s_wfinal[0 * N + cc + j], fin[0]);
-                                fin[1] = fmaf(v[j], s_wfinal[1 * N + cc + j], fin[1]);
-                                fin[2] = fmaf(v[j], s_wfinal[2 * N + cc + j], fin[2]);
-                            }
-                        }
-                        if (ep.out) {
-                            if (ep.round_tf32) {
-#pragma unroll
-                                for (int j = 0; j < 16; ++j) v[j] = round_tf32(v[j]);
-                            }
-                            float4* o4 = reinterpret_cast<float4*>(ep.out + off);
-#pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                o4[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                        }
+                        store_tile(&tm_out, cc, v);
                     }
                 };
                 {
-                    uint32_t r0[16], r1[16];
-                    if (cc < N) tmem_ld16_issue(taddr + cc, r0);
-                    while (cc < N) {
-                        tmem_ld16_wait(r0);
-                        if (cc + 32 < N) tmem_ld16_issue(taddr + cc + 32, r1);
-                        process(cc, r0);
-                        cc += 32;
-                        if (cc >= N) break;
-                        tmem_ld16_wait(r1);
-                        if (cc + 32 < N) tmem_ld16_issue(taddr + cc + 32, r0);
-                        process(cc, r1);
-                        cc += 32;
+                    // Drain first, compute later: the whole column share of this warp (<= 5 chunks) moves to
+                    // registers and the TMEM slot goes straight back to the MMA warp, so the next tile's main loop
+                    // overlaps the epilogue arithmetic of BOTH halves instead of waiting for the first one.
+                    uint32_t r[kMaxN / (2 * kEpiChunk)][16];
+#pragma unroll
+                    for (int i = 0; i < kMaxN / (2 * kEpiChunk); ++i)
+                        if (cc + i * 2 * kEpiChunk < N) tmem_ld16_issue(taddr + cc + i * 2 * kEpiChunk, r[i]);
+#pragma unroll
+                    for (int i = 0; i < kMaxN / (2 * kEpiChunk); ++i)
+                        if (cc + i * 2 * kEpiChunk < N) tmem_ld16_wait(r[i]);
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (TWO) mbar_arrive_remote(&tempty_bar[slot], 0);   // the leader's MMA warp waits for both CTAs
+                        else mbar_arrive(&tempty_bar[slot]);
                     }
-                }
-                // every tcgen05.ld of this slot has completed (tmem_ld16_wait): hand it back
-                tc_fence_before_sync();
-                __syncwarp();
-                if (lane == 0) {
-                    if (TWO) mbar_arrive_remote(&tempty_bar[slot], 0);   // the leader's MMA warp waits for both CTAs
-                    else mbar_arrive(&tempty_bar[slot]);
+#pragma unroll
+                    for (int i = 0; i < kMaxN / (2 * kEpiChunk); ++i)
+                        if (cc + i * 2 * kEpiChunk < N) process(cc + i * 2 * kEpiChunk, r[i]);
                 }
 
                 if (ep.w_final) {
@@ -455,6 +505,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                 }
             }
         }
+        if (lane == 0) bulk_wait_group_read<0>();   // the staging tiles are read until the last store has drained
+        __syncwarp();
     }
 
     // ---------------------------------------------------------------- teardown
@@ -507,14 +559,28 @@ int tc_conv_prepare(const ConvProblem& p, TcConvOp* op) {
         op->tm_ares = op->tm_a;
         op->tm_bres = op->tm_b;
     }
-    // weight ring: as many boxes as fit beside the 3 activation slots (at most kMaxStagesB)
+    // epilogue tiles: (16 ch, 16 w, 2 h) boxes, 64B swizzle; unused maps alias the activation map
+    {
+        const float* in_stream = p.ep.res_add ? p.ep.res_add : p.ep.dgelu_z;
+        const float* ptrs[3] = {p.ep.out, p.ep.out_pre, in_stream};
+        CUtensorMap* maps[3] = {&op->tm_out, &op->tm_pre, &op->tm_in};
+        for (int i = 0; i < 3; ++i) {
+            if (ptrs[i])
+                SINDDM_TRY(make_tmap_nhwc(maps[i], ptrs[i], p.B, p.H, p.W, p.N, kEpiChunk, kTileW, 2,
+                                          CU_TENSOR_MAP_SWIZZLE_64B));
+            else
+                *maps[i] = op->tm_a;
+        }
+    }
+    // weight ring: as many boxes as fit beside the 3 activation slots and the epilogue tiles (at most kMaxStagesB)
     op->stage_bytes = (int)align_up((size_t)(p.N / cs) * kKC * 4, 1024);
-    const int budget = device_info().max_smem_optin - 1024 /*alignment slack*/ - kTailBytes - kStagesA * kABytes;
+    const int budget =
+        device_info().max_smem_optin - 1024 /*alignment slack*/ - kTailBytes - kStagesA * kABytes - kEpiBytes;
     int nst = budget / op->stage_bytes;
     if (nst > kMaxStagesB) nst = kMaxStagesB;
     SINDDM_REQUIRE(nst >= 3, "tc_conv: not enough shared memory for the weight ring");
     op->nstages = nst;
-    op->smem_bytes = kStagesA * kABytes + nst * op->stage_bytes + kTailBytes + 1024;
+    op->smem_bytes = kStagesA * kABytes + nst * op->stage_bytes + kEpiBytes + kTailBytes + 1024;
     op->tiles_w = ceil_div(p.W, kTileW);
     op->tiles_h = ceil_div(p.H, kTileH);
     op->ntiles = op->tiles_w * op->tiles_h * p.B;
@@ -554,6 +620,10 @@ int tc_conv_launch(const TcConvOp& op, cudaStream_t stream) {
     a.idesc = umma_idesc_tf32(op.cs == 2 ? 256 : 128, p.N, 0, 0);
     a.w_blk = p.w_blocked ? p.w : nullptr;
     a.wres_blk = p.w_blocked ? p.w_res : nullptr;
+    {
+        const char* e = getenv("SINDDM_TC_DEBUG");   // diagnostic runs only: results are wrong when set
+        a.dbg = e ? atoi(e) : 0;
+    }
     a.ep = p.ep;
     // algorithmic work: real pixels x N x (taps*Cin + Cres) MACs
     prof_begin(stream, 0, 2.0 * (double)p.B * p.H * p.W * p.N * ((double)p.ntaps * p.Cin + a.Cres));
@@ -571,14 +641,16 @@ int tc_conv_launch(const TcConvOp& op, cudaStream_t stream) {
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        cudaError_t lerr = cudaLaunchKernelEx(&cfg, tc_conv_kernel<true>, op.tm_a, op.tm_ares, op.tm_b, op.tm_bres, a);
+        cudaError_t lerr = cudaLaunchKernelEx(&cfg, tc_conv_kernel<true>, op.tm_a, op.tm_ares, op.tm_b, op.tm_bres,
+                                              op.tm_out, op.tm_pre, op.tm_in, a);
         if (lerr != cudaSuccess) {
             prof_end(stream);
             set_error("tc_conv (cta pair) launch failed: %s", cudaGetErrorString(lerr));
             return SINDDM_ERR_CUDA;
         }
     } else {
-        tc_conv_kernel<false><<<op.grid, kThreads, op.smem_bytes, stream>>>(op.tm_a, op.tm_ares, op.tm_b, op.tm_bres, a);
+        tc_conv_kernel<false><<<op.grid, kThreads, op.smem_bytes, stream>>>(op.tm_a, op.tm_ares, op.tm_b, op.tm_bres,
+                                                                            op.tm_out, op.tm_pre, op.tm_in, a);
     }
     prof_end(stream);
     SINDDM_CUDA_OK(cudaGetLastError());
