@@ -52,12 +52,13 @@ constexpr int kTmemCols = 512;
 constexpr int kSlots = 3;
 constexpr int kStagesA = 3;   // activation (halo box) ring
 constexpr int kMaxStagesB = 8;   // weight box ring
-// epilogue staging: every epilogue warp owns three [32 px][16 ch] tiles (64B-swizzled, 2 KiB): one filled by a TMA
-// load of the streamed operand (residual / pre-activation), two drained by TMA stores of the results
+// epilogue staging: every epilogue warp owns two [32 px][16 ch] tiles (64B-swizzled, 2 KiB).  Layers that stream an
+// operand in (residual / saved pre-activation) have one result: tile 0 receives the TMA load, tile 1 is drained by
+// the TMA store.  Layers without one may have two results (pre-activation + activation): both tiles are store buffers.
 constexpr int kEpiChunk = 16;
 constexpr int kEpiTileBytes = 32 * kEpiChunk * 4;
-constexpr int kEpiWarpBytes = 3 * kEpiTileBytes;
-constexpr int kEpiBytes = (kEpiThreads / 32) * kEpiWarpBytes;   // 48 KiB
+constexpr int kEpiWarpBytes = 2 * kEpiTileBytes;
+constexpr int kEpiBytes = (kEpiThreads / 32) * kEpiWarpBytes;   // 32 KiB
 
 struct KernelArgs {
     int B, H, W;
@@ -70,15 +71,15 @@ struct KernelArgs {
     const float* w_blk;        // non-null: weights in the blocked pre-swizzled layout [tap][chunk][N][32] ...
     const float* wres_blk;     // ... (and the residual 1x1 weights [chunk][N][32]): boxes come by 1-D bulk copy
     uint32_t idesc;
-    int dbg;                   // diagnostics (SINDDM_TC_DEBUG): 1 = no operand loads, 2 = no epilogue traffic, 4 = no MMAs
+    int dbg;                   // diagnostics (SINDDM_TC_DEBUG): 1 = no operand loads, 2 = no epilogue traffic, 4 = no MMAs, 8 = stage but do not store
     ConvEpilogue ep;
 };
 
 // smem tail (after the 1024-aligned stage ring):
 //   uint64 fullA[3], emptyA[3], fullB[8], emptyB[8], tfull[3], tempty[3], epi_in[8]; uint32 tmem_slot[4];
-//   float bias[kMaxN], wres3[kMaxN*3], wfinal[3*kMaxN], bfinal[4]
+//   float bias[kMaxN], wres3[kMaxN*3] (aliased by wfinal[3*kMaxN]: no layer has both), bfinal[4], fin[128*3]
 constexpr int kTailBytes = (2 * kStagesA + 2 * kMaxStagesB + 2 * kSlots + kEpiThreads / 32) * 8 + 16 +
-                           (kMaxN + kMaxN * 3 + 3 * kMaxN + 4 + 128 * 3) * 4 + 64;
+                           (kMaxN + kMaxN * 3 + 4 + 128 * 3) * 4 + 64;
 
 // TWO = true: CTA pairs (cluster of 2, cta_group::2): one M=256 MMA covers the same half of BOTH CTAs' tiles,
 // each CTA stages only half of the weight rows, and only the leader CTA issues MMAs.
@@ -104,7 +105,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_in_bar + kEpiThreads / 32);
     float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
     float* s_wres3 = s_bias + kMaxN;
-    float* s_wfinal = s_wres3 + kMaxN * 3;
+    float* s_wfinal = s_wres3;   // the 3-channel residual weights and the fused final conv never meet in one layer
     float* s_bfinal = s_wfinal + 3 * kMaxN;
 
     // warp index through a shuffle so the compiler can prove the role branches are warp-uniform
@@ -169,9 +170,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     // Roles 0 and 1 run their loops with ALL 32 lanes (uniform control flow); TMA, MMA and commit instructions
     // elect their single issuing lane inside the asm (common.cuh) -- see elect_one_sync() for why.
     // the launch gives every thread 168 registers; the producer / MMA warpgroup hands most of its share to the
-    // epilogue warpgroups, which keep a whole half tile's accumulator columns in registers (384*168 = 128*56 + 256*224)
+    // epilogue warpgroups, which keep a whole half tile's accumulator columns in registers (384*168 = 128*88 + 256*208)
     if (warp < kEpiWarp0) {
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 72;" ::: "memory");
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 88;" ::: "memory");
       if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
         int sa_i = 0, sb_i = 0;
@@ -269,30 +270,61 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                 const int kys = main ? nky : 1;
                 mbar_wait(&fulla_bar[sa_i], pha);
                 const uint32_t sa = smem_u32(smem + (size_t)sa_i * kABytes);
-                for (int ky = 0; ky < kys; ++ky) {
-                    mbar_wait(&fullb_bar[sb_i], phb);
-                    tc_fence_after_sync();
-                    // vertical tap = row offset into the halo box; the 1x1 / residual case reads the centre rows
-                    const int row0 = (main && nky == 3) ? ky : 1;
-                    const uint32_t a0 = ((sa + (uint32_t)row0 * kRowBytes) >> 4) & 0x3FFFu;
-                    const uint32_t a1 = ((sa + (uint32_t)(row0 + 8) * kRowBytes) >> 4) & 0x3FFFu;
-                    const uint32_t bb = (smem_u32(smem_b + (size_t)sb_i * a.bbox_bytes) >> 4) & 0x3FFFu;
-                    const uint32_t acc = (it | ky) != 0 ? 1u : 0u;
-                    // K slices advance by 32 B inside the 128B-swizzled rows: +2 in the encoded start address
-                    if (TWO) {
-                        umma_tf32_ss_x4_2sm(d0, a0, bb, desc_hi, 2u, a.idesc, acc, nmma);
-                        umma_tf32_ss_x4_2sm(d1, a1, bb, desc_hi, 2u, a.idesc, acc, nmma);
-                        umma_commit_2sm_elect(&emptyb_bar[sb_i]);
-                    } else {
-                        if (!(a.dbg & 4)) {
-                            umma_tf32_ss_x4(d0, a0, bb, desc_hi, 2u, a.idesc, acc, nmma);
-                            umma_tf32_ss_x4(d1, a1, bb, desc_hi, 2u, a.idesc, acc, nmma);
+                // vertical tap = row offset into the halo box; the 1x1 / residual case reads the centre rows.
+                // K slices advance by 32 B inside the 128B-swizzled rows: +2 in the encoded start address
+                auto a_desc = [&](int ky, int half) {
+                    const int row0 = ((main && nky == 3) ? ky : 1) + 8 * half;
+                    return ((sa + (uint32_t)row0 * kRowBytes) >> 4) & 0x3FFFu;
+                };
+                auto b_desc = [&](int slot_b) {
+                    return (smem_u32(smem_b + (size_t)slot_b * a.bbox_bytes) >> 4) & 0x3FFFu;
+                };
+                if (TWO || it != nst - 1) {
+                    for (int ky = 0; ky < kys; ++ky) {
+                        mbar_wait(&fullb_bar[sb_i], phb);
+                        tc_fence_after_sync();
+                        const uint32_t a0 = a_desc(ky, 0), a1 = a_desc(ky, 1), bb = b_desc(sb_i);
+                        const uint32_t acc = (it | ky) != 0 ? 1u : 0u;
+                        if (TWO) {
+                            umma_tf32_ss_x4_2sm(d0, a0, bb, desc_hi, 2u, a.idesc, acc, nmma);
+                            umma_tf32_ss_x4_2sm(d1, a1, bb, desc_hi, 2u, a.idesc, acc, nmma);
+                            umma_commit_2sm_elect(&emptyb_bar[sb_i]);
+                        } else {
+                            if (!(a.dbg & 4)) {
+                                umma_tf32_ss_x4(d0, a0, bb, desc_hi, 2u, a.idesc, acc, nmma);
+                                umma_tf32_ss_x4(d1, a1, bb, desc_hi, 2u, a.idesc, acc, nmma);
+                            }
+                            umma_commit_elect(&emptyb_bar[sb_i]);
                         }
-                        umma_commit_elect(&emptyb_bar[sb_i]);
+                        if (++sb_i == a.nstages_b) {
+                            sb_i = 0;
+                            phb ^= 1u;
+                        }
                     }
-                    if (++sb_i == a.nstages_b) {
-                        sb_i = 0;
-                        phb ^= 1u;
+                } else {
+                    // last stage of the tile: finish the first half on its own, so that the epilogue drains its
+                    // accumulator (and returns the TMEM slot the next tile needs) while the second half completes
+                    int sb = sb_i;
+                    uint32_t ph = phb;
+                    for (int ky = 0; ky < kys; ++ky) {
+                        mbar_wait(&fullb_bar[sb], ph);
+                        tc_fence_after_sync();
+                        if (!(a.dbg & 4))
+                            umma_tf32_ss_x4(d0, a_desc(ky, 0), b_desc(sb), desc_hi, 2u, a.idesc, (it | ky) != 0 ? 1u : 0u, nmma);
+                        if (++sb == a.nstages_b) {
+                            sb = 0;
+                            ph ^= 1u;
+                        }
+                    }
+                    umma_commit_elect(&tfull_bar[s0]);
+                    for (int ky = 0; ky < kys; ++ky) {
+                        if (!(a.dbg & 4))
+                            umma_tf32_ss_x4(d1, a_desc(ky, 1), b_desc(sb_i), desc_hi, 2u, a.idesc, (it | ky) != 0 ? 1u : 0u, nmma);
+                        umma_commit_elect(&emptyb_bar[sb_i]);
+                        if (++sb_i == a.nstages_b) {
+                            sb_i = 0;
+                            phb ^= 1u;
+                        }
                     }
                 }
                 if (TWO) umma_commit_2sm_elect(&emptya_bar[sa_i]);
@@ -306,13 +338,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                 umma_commit_2sm_elect(&tfull_bar[s0]);
                 umma_commit_2sm_elect(&tfull_bar[s1]);
             } else {
-                umma_commit_elect(&tfull_bar[s0]);
-                umma_commit_elect(&tfull_bar[s1]);
+                umma_commit_elect(&tfull_bar[s1]);   // s0 was committed inside the last stage
             }
         }
       }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 216;" ::: "memory");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 208;" ::: "memory");
         // ------------------------------------------------------------ epilogue warps (8)
         // warp w reads TMEM lane quarter (w & 3) = 32 pixels = a 16 x 2 pixel strip; the two warps of a quarter
         // split the 16-column chunks (even / odd).  Results never touch the LSU on their way out: a lane owns one
@@ -327,7 +358,6 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         const ConvEpilogue& ep = a.ep;
         float* s_fin = reinterpret_cast<float*>(s_bfinal + 4);   // [128][3] partial final-conv sums of group 1
         uint8_t* stg_in = smem_epi + (size_t)ew * kEpiWarpBytes;
-        uint8_t* stg_out = stg_in + kEpiTileBytes;
         uint64_t* in_bar = &epi_in_bar[ew];
         // 64B swizzle: the 16-byte unit index of a row is XORed with bits 7-8 of the row's byte offset
         const uint32_t lrow = (uint32_t)lane * 64u, swz = (uint32_t)(lane >> 1) & 3u;
@@ -372,9 +402,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(slot * a.slot_stride);
 
                 auto store_tile = [&](const CUtensorMap* map, const int cc, const float (&v)[16]) {
-                    uint8_t* buf = stg_out + obuf * kEpiTileBytes;
+                    // with a streamed operand tile 1 is the only store buffer, otherwise the two tiles alternate
+                    uint8_t* buf = stg_in + (gsrc ? 1 : obuf) * kEpiTileBytes;
                     obuf ^= 1;
-                    if (lane == 0) bulk_wait_group_read<1>();   // the store issued from this buffer two stores ago
+                    if (lane == 0) {   // the previous store that read this buffer must have drained it
+                        if (gsrc) bulk_wait_group_read<0>();
+                        else bulk_wait_group_read<1>();
+                    }
                     __syncwarp();
 #pragma unroll
                     for (uint32_t q = 0; q < 4; ++q)
@@ -382,7 +416,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                             make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
                     fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0) {
+                    if (lane == 0 && !(a.dbg & 8)) {
                         tma_store_4d(map, buf, cc, w0, hq, b);
                         bulk_commit_group();
                     }
@@ -543,6 +577,9 @@ int tc_conv_prepare(const ConvProblem& p, TcConvOp* op) {
     SINDDM_REQUIRE(tc_conv_supported(p), "tc_conv: unsupported shape Cin=%d Cres=%d N=%d ntaps=%d", p.Cin, p.Cres,
                    p.N, p.ntaps);
     SINDDM_REQUIRE(device_info().initialized, "sinddm_init() has not been called");
+    SINDDM_REQUIRE(!(p.ep.w_res3 && p.ep.w_final), "tc_conv: w_res3 and w_final cannot be fused into one layer");
+    SINDDM_REQUIRE(!((p.ep.res_add || p.ep.dgelu_z) && p.ep.out_pre && p.ep.out),
+                   "tc_conv: a streamed epilogue operand allows one result tensor");
     op->p = p;
     // CTA pairs (SINDDM_TC_2SM=0 disables): each CTA stages N/2 weight rows, which must be whole 8-row atoms
     op->cs = (two_sm_setting() && p.N % 16 == 0 && !p.w_blocked) ? 2 : 1;

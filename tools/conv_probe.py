@@ -52,4 +52,6 @@ for name, kw in (("fwd gelu+pre (net[0])", dict(gelu=True, save_pre=True, round_
     run("no MMAs (loads + epilogue)", 4, **kw)
     run("loads only", 6, **kw)
     run("epilogue only", 5, **kw)
+    run("epilogue only, staged but not stored", 13, **kw)
+    run("barrier chain only", 7, **kw)
 os.environ["SINDDM_TC_DEBUG"] = "0"
