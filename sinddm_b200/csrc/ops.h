@@ -82,8 +82,8 @@ struct WgradProblem {
 struct TcWgradOp {
     CUtensorMap tm_x, tm_dy;
     WgradProblem p;
-    int cxk, cyk, nchunks, tpc, ngroups, wt, nks, col_stride, tmem_cols;
-    int stage_bytes, nstages, smem_bytes;
+    int cxk, cyk, nregions, nreg_cta, ntile, ngroups, wt, nks, pw, rb, col_stride, tmem_cols;
+    int x_bytes, stage_bytes, nstages, smem_bytes;
 };
 bool tc_wgrad_supported(int Cx, int Cy);
 int tc_wgrad_nsplit(int B, int H, int W, int Cx, int Cy, int ntaps);

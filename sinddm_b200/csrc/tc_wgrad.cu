@@ -6,16 +6,19 @@
 //   dW[tap][ci][co] = sum_p x[p (+) tap][ci] * dy[p][co]
 //
 //   GEMM view      K = pixels, walked in steps of one 32-pixel row segment (b, h, 32 w)
-//                  M = the flattened (tap, 32-channel chunk of x) axis, 4 chunks = one 128-row UMMA tile
-//                      -> rows of one tile may come from different taps (different shifted boxes of x),
-//                         which keeps M tiles full even though Cx is 80/160;
-//                  N = Cy (all output channels of dy, one UMMA N).
-//   operands       both are "MN-major" (channels contiguous, pixels strided): each 32px x 32ch fp32 box
-//                  is TMA-loaded with the 128B/32B-atom swizzle, the only smem layout the tensor core
-//                  accepts for MN-major tf32.  Shifted x boxes use out-of-bounds zero fill for padding.
-//   accumulators   tpc M-tiles x Cy fp32 columns in TMEM (<= 512), resident for the whole K range.
-//   grid           ngroups (M-tile groups) x nsplit (pixel ranges); each CTA writes its partial
-//                  [tap][ci][co] block, a second kernel (wgrad_reduce) sums the splits in fixed order.
+//                  M = channels of x (32-channel chunks), N = Cy (all channels of dy, one UMMA N).
+//   operands       both are "MN-major" (channels contiguous, pixels strided): [pixels][32 ch] fp32 boxes, TMA-loaded
+//                  with the 128B/32B-atom swizzle, the only smem layout the tensor core accepts for MN-major tf32.
+//   halo sharing   the kernel is bound by the bytes entering shared memory, so the three horizontal taps share
+//                  their data: a "region" is the (32 ch, 34 px) box of one image row h+dy starting at w0-1
+//                  (out-of-image pixels zero-filled by TMA = the convolution's padding), and tap dx is the same
+//                  box read from pixel 1+dx on -- the operand descriptor simply starts 128 B (one pixel) later.
+//                  A CTA stages up to 4 regions = (vertical tap, channel chunk) pairs per K step and owns the
+//                  3 x (4 x 32) x Cy accumulators of their three horizontal taps: 3 MMA tiles from 4 boxes
+//                  instead of 12 boxes (1.8x fewer bytes per FLOP at 160 channels, 2x at Cy = 80).
+//   accumulators   up to 3 tiles x Cy fp32 columns in TMEM, resident for the CTA's whole pixel range.
+//   grid           nsplit (pixel ranges) x ngroups (region sets); each CTA writes its partial [tap][ci][co] block,
+//                  a second kernel (wgrad_reduce) sums the splits in fixed order (deterministic).
 #include "common.cuh"
 #include "ops.h"
 
@@ -25,18 +28,25 @@ namespace {
 
 constexpr int kKP = 32;                   // pixels per K step
 constexpr int kCC = 32;                   // channels per chunk box
-constexpr int kBoxBytes = kKP * kCC * 4;  // 4 KiB
+constexpr int kRowBytes = kCC * 4;        // one pixel of a box: 128 B
+constexpr int kDyBoxBytes = kKP * kRowBytes;   // 4 KiB
+constexpr int kRegPerTile = 4;            // 32-channel regions per M = 128 tile
+constexpr int kMaxTiles = 3;
 constexpr int kThreads = 192;
 
 struct KernelArgs {
     int B, H, W;
     int Cx, Cy, ntaps;
-    int cxk, cyk, nchunks;       // chunks per tap (x), chunks of dy, ntaps*cxk
-    int tpc, ngroups, nsplit;    // M tiles per CTA, groups, pixel splits
+    int cxk, cyk;
+    int nregions;                // 3 * cxk (3x3: one per vertical tap and chunk) or cxk (1x1)
+    int nreg_cta;                // regions staged per CTA
+    int ntile;                   // accumulator tiles per CTA: the 3 horizontal taps (3x3) or ceil(nreg_cta / 4) (1x1)
+    int nsplit;
     int wt, nks;                 // 32-px segments per row, total K steps
-    int col_stride;              // TMEM columns between M-tile accumulators
+    int rb;                      // bytes between region boxes in shared memory
+    int col_stride;              // TMEM columns between accumulator tiles
     int tmem_cols;
-    int nstages, stage_bytes;
+    int nstages, stage_bytes, x_bytes;
     uint32_t idesc;
     float* partial;
 };
@@ -56,17 +66,16 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     const int lane = threadIdx.x & 31;
     const int group = blockIdx.y;
     const int split = blockIdx.x;
+    const bool k3 = a.ntaps == 9;
 
     // K-step range of this split (balanced, contiguous)
     const int ks_begin = (int)(((long long)a.nks * split) / a.nsplit);
     const int ks_end = (int)(((long long)a.nks * (split + 1)) / a.nsplit);
 
-    // chunk slots of this group: slot q <-> global chunk id g0 + q, valid while < nchunks
-    const int nslots = a.tpc * 4;
-    const int g0 = group * nslots;
-    int nvalid = a.nchunks - g0;
-    if (nvalid > nslots) nvalid = nslots;
-    const int ntile_valid = (nvalid + 3) >> 2;
+    // regions of this group: local q <-> global region r0 + q
+    const int r0 = group * a.nreg_cta;
+    int nvalid = a.nregions - r0;
+    if (nvalid > a.nreg_cta) nvalid = a.nreg_cta;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_x);
@@ -84,13 +93,12 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int a_bytes = nslots * kBoxBytes;  // x region of a stage; dy region follows
-
     // Roles 0 and 1 run with all 32 lanes in uniform control flow; the issuing lane is elected inside the asm.
     if (warp == 0) {
         int stage = 0;
         uint32_t phase = 0;
-        const uint32_t tx_bytes = (uint32_t)(nvalid + a.cyk) * kBoxBytes;
+        const int pw = k3 ? kKP + 2 : kKP;
+        const uint32_t tx_bytes = (uint32_t)(nvalid * pw * kRowBytes + a.cyk * kDyBoxBytes);
         for (int ks = ks_begin; ks < ks_end; ++ks) {
             const int per_img = a.H * a.wt;
             const int b = ks / per_img;
@@ -99,20 +107,15 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             const int w0 = (r - h * a.wt) * kKP;
             mbar_wait(&empty_bar[stage], phase ^ 1u);
             uint8_t* sx = smem + (size_t)stage * a.stage_bytes;
-            uint8_t* sy = sx + a_bytes;
+            uint8_t* sy = sx + a.x_bytes;
             mbar_arrive_expect_tx_w(&full_bar[stage], tx_bytes);
             for (int j = 0; j < a.cyk; ++j)
-                tma_load_4d_w(sy + j * kBoxBytes, &tm_dy, &full_bar[stage], j * kCC, w0, h, b);
+                tma_load_4d_w(sy + j * kDyBoxBytes, &tm_dy, &full_bar[stage], j * kCC, w0, h, b);
             for (int q = 0; q < nvalid; ++q) {
-                const int gq = g0 + q;
-                const int tap = gq / a.cxk;
-                const int j = gq - tap * a.cxk;
-                int dy = 0, dx = 0;
-                if (a.ntaps == 9) {
-                    dy = tap / 3 - 1;
-                    dx = tap % 3 - 1;
-                }
-                tma_load_4d_w(sx + q * kBoxBytes, &tm_x, &full_bar[stage], j * kCC, w0 + dx, h + dy, b);
+                const int rg = r0 + q;
+                const int dyi = rg / a.cxk;              // vertical tap (3x3) -- always 0 for 1x1
+                const int j = rg - dyi * a.cxk;
+                tma_load_4d_w(sx + q * a.rb, &tm_x, &full_bar[stage], j * kCC, k3 ? w0 - 1 : w0, k3 ? h + dyi - 1 : h, b);
             }
             if (++stage == a.nstages) {
                 stage = 0;
@@ -122,20 +125,27 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     } else if (warp == 1) {
         int stage = 0;
         uint32_t phase = 0;
-        // MN-major, 128B swizzle with 32B atoms: 4-pixel atoms are 512 B apart (SBO), 32-channel chunk boxes are
-        // kBoxBytes apart (LBO, bits 16.. of the low word); 8 pixels per MMA = 1024 B = +64 in the start address.
-        const uint64_t proto = umma_smem_desc(0, kBoxBytes, 512, UMMA_LAYOUT_SW128_B32);
-        const uint32_t desc_hi = (uint32_t)(proto >> 32);
-        const uint32_t lbo_lo = (uint32_t)proto;
+        // MN-major, 128B swizzle with 32B atoms: 4-pixel atoms are 512 B apart (SBO); the 32-channel boxes of one
+        // operand are LBO apart (bits 16.. of the low word): one region stride for x, one box for dy.
+        // 8 pixels per MMA = 1024 B = +64 in the start address.
+        const uint64_t proto_x = umma_smem_desc(0, (uint32_t)a.rb, 512, UMMA_LAYOUT_SW128_B32);
+        const uint64_t proto_y = umma_smem_desc(0, kDyBoxBytes, 512, UMMA_LAYOUT_SW128_B32);
+        const uint32_t desc_hi = (uint32_t)(proto_y >> 32);
+        const uint32_t lbo_x = (uint32_t)proto_x, lbo_y = (uint32_t)proto_y;
         for (int ks = ks_begin; ks < ks_end; ++ks) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after_sync();
             const uint32_t sx = smem_u32(smem + (size_t)stage * a.stage_bytes);
-            const uint32_t sy = sx + a_bytes;
+            const uint32_t sy = sx + (uint32_t)a.x_bytes;
             const uint32_t acc = (ks != ks_begin) ? 1u : 0u;
-            const uint32_t b_lo = lbo_lo | ((sy >> 4) & 0x3FFFu);
-            for (int i = 0; i < ntile_valid; ++i) {
-                const uint32_t a_lo = lbo_lo | (((sx + (uint32_t)i * 4u * kBoxBytes) >> 4) & 0x3FFFu);
+            const uint32_t b_lo = lbo_y | ((sy >> 4) & 0x3FFFu);
+            for (int i = 0; i < a.ntile; ++i) {
+                // 3x3: tile i = horizontal tap i, the box read from pixel i on;  1x1: tile i = regions 4i..4i+3
+                const uint32_t start = k3 ? sx + (uint32_t)i * kRowBytes : sx + (uint32_t)(i * kRegPerTile * a.rb);
+                const uint32_t a_lo = lbo_x | ((start >> 4) & 0x3FFFu);
+                // A start that is a whole number of pixels (128 B) into the box needs no base-offset field: the
+                // tensor core applies the swizzle to absolute shared-memory address bits, like TMA did on the way
+                // in (verified on B200: base offset 0 is bit-compatible with the aligned kernel, non-zero is wrong)
                 umma_tf32_ss_x4(tmem_base + (uint32_t)(i * a.col_stride), a_lo, b_lo, desc_hi, 64u, a.idesc, acc,
                                 kKP / 8);
             }
@@ -152,12 +162,14 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         const int row = quarter * 32 + lane;
         mbar_wait(done_bar, 0);
         tc_fence_after_sync();
-        for (int i = 0; i < ntile_valid; ++i) {
-            const int v = (group * a.tpc + i) * 128 + row;   // virtual (tap, chunk, channel) row
-            const int gq = v >> 5;
-            const int tap = gq / a.cxk;
-            const int ci = (gq - tap * a.cxk) * kCC + (v & 31);
-            const bool valid = (gq < a.nchunks) && (ci < a.Cx);
+        for (int i = 0; i < a.ntile; ++i) {
+            const int q = (k3 ? 0 : i * kRegPerTile) + (row >> 5);   // local region of this row
+            const int rg = r0 + q;
+            const int dyi = rg / a.cxk;
+            const int j = rg - dyi * a.cxk;
+            const int tap = k3 ? dyi * 3 + i : 0;
+            const int ci = j * kCC + (row & 31);
+            const bool valid = (q < nvalid) && (ci < a.Cx);
             float* dst = a.partial + (((size_t)split * a.ntaps + tap) * a.Cx + ci) * a.Cy;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(i * a.col_stride);
             for (int cc = 0; cc < a.Cy; cc += 16) {
@@ -166,8 +178,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 if (valid) {
                     float4* o4 = reinterpret_cast<float4*>(dst + cc);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        o4[q] = make_float4(vals[4 * q], vals[4 * q + 1], vals[4 * q + 2], vals[4 * q + 3]);
+                    for (int t = 0; t < 4; ++t)
+                        o4[t] = make_float4(vals[4 * t], vals[4 * t + 1], vals[4 * t + 2], vals[4 * t + 3]);
                 }
             }
         }
@@ -182,22 +194,37 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
 }
 
 struct Shape {
-    int cxk, cyk, nchunks, tpc, ngroups, col_stride, tmem_cols, wt, nks;
+    int cxk, cyk, nregions, nreg_cta, ntile, ngroups, col_stride, tmem_cols, wt, nks, pw, rb, x_bytes;
 };
 
 Shape make_shape(int B, int H, int W, int Cx, int Cy, int ntaps) {
     Shape s;
     s.cxk = ceil_div(Cx, kCC);
     s.cyk = ceil_div(Cy, kCC);
-    s.nchunks = ntaps * s.cxk;
     s.col_stride = (int)align_up((size_t)Cy, 32);
-    int tpc = 512 / s.col_stride;
-    if (tpc > 3) tpc = 3;                    // smem: 3 tiles x 4 boxes + dy boxes per stage
-    const int ntile = ceil_div(s.nchunks, 4);
-    if (tpc > ntile) tpc = ntile;
-    s.tpc = tpc;
-    s.ngroups = ceil_div(ntile, tpc);
-    int cols = tpc * s.col_stride;
+    if (ntaps == 9) {
+        s.nregions = 3 * s.cxk;
+        // fewest CTAs groups first, then the fewest staged regions per group
+        int best = kRegPerTile, best_groups = ceil_div(s.nregions, kRegPerTile);
+        for (int n = kRegPerTile - 1; n >= 1; --n)
+            if (ceil_div(s.nregions, n) <= best_groups) best = n;
+        s.nreg_cta = best;
+        s.ntile = 3;
+        s.pw = kKP + 2;
+        s.x_bytes = 0;   // set below
+    } else {
+        s.nregions = s.cxk;
+        const int cap = kRegPerTile * kMaxTiles;
+        const int groups = ceil_div(s.nregions, cap);
+        s.nreg_cta = ceil_div(s.nregions, groups);
+        s.ntile = ceil_div(s.nreg_cta, kRegPerTile);
+        s.pw = kKP;
+    }
+    s.ngroups = ceil_div(s.nregions, s.nreg_cta);
+    s.rb = (int)align_up((size_t)s.pw * kRowBytes, 1024);
+    // every tile's descriptor spans 4 regions: keep that reach inside the x area of the stage
+    s.x_bytes = (ntaps == 9 ? kRegPerTile : s.ntile * kRegPerTile) * s.rb;
+    const int cols = s.ntile * s.col_stride;
     s.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
     s.wt = ceil_div(W, kKP);
     s.nks = B * H * s.wt;
@@ -231,19 +258,23 @@ int tc_wgrad_prepare(const WgradProblem& p, TcWgradOp* op) {
     op->p = p;
     op->cxk = s.cxk;
     op->cyk = s.cyk;
-    op->nchunks = s.nchunks;
-    op->tpc = s.tpc;
+    op->nregions = s.nregions;
+    op->nreg_cta = s.nreg_cta;
+    op->ntile = s.ntile;
     op->ngroups = s.ngroups;
     op->wt = s.wt;
     op->nks = s.nks;
+    op->pw = s.pw;
+    op->rb = s.rb;
     op->col_stride = s.col_stride;
     op->tmem_cols = s.tmem_cols;
-    SINDDM_TRY(make_tmap_nhwc(&op->tm_x, p.x, p.B, p.H, p.W, p.Cx, kCC, kKP, 1, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+    op->x_bytes = s.x_bytes;
+    SINDDM_TRY(make_tmap_nhwc(&op->tm_x, p.x, p.B, p.H, p.W, p.Cx, kCC, s.pw, 1, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
     SINDDM_TRY(make_tmap_nhwc(&op->tm_dy, p.dy, p.B, p.H, p.W, p.Cy, kCC, kKP, 1, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
-    op->stage_bytes = (s.tpc * 4 + s.cyk) * kBoxBytes;
+    op->stage_bytes = s.x_bytes + s.cyk * kDyBoxBytes;
     const int tail = 8 * 8 * 2 + 8 + 16;
     int nst = (device_info().max_smem_optin - 1024 - tail) / op->stage_bytes;
-    if (nst > 6) nst = 6;
+    if (nst > 8) nst = 8;
     SINDDM_REQUIRE(nst >= 2, "tc_wgrad: not enough shared memory");
     op->nstages = nst;
     op->smem_bytes = nst * op->stage_bytes + tail + 1024;
@@ -267,16 +298,18 @@ int tc_wgrad_launch(const TcWgradOp& op, cudaStream_t stream) {
     a.ntaps = p.ntaps;
     a.cxk = op.cxk;
     a.cyk = op.cyk;
-    a.nchunks = op.nchunks;
-    a.tpc = op.tpc;
-    a.ngroups = op.ngroups;
+    a.nregions = op.nregions;
+    a.nreg_cta = op.nreg_cta;
+    a.ntile = op.ntile;
     a.nsplit = p.nsplit;
     a.wt = op.wt;
     a.nks = op.nks;
+    a.rb = op.rb;
     a.col_stride = op.col_stride;
     a.tmem_cols = op.tmem_cols;
     a.nstages = op.nstages;
     a.stage_bytes = op.stage_bytes;
+    a.x_bytes = op.x_bytes;
     a.idesc = umma_idesc_tf32(128, p.Cy, 1, 1);
     a.partial = p.partial;
     dim3 grid(p.nsplit, op.ngroups);
