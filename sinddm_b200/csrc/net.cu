@@ -234,6 +234,7 @@ int plan_build(Plan* pl, int B, int H, int W, int dim, int channels, int math, i
         b.tc_c1 = use_tc_conv(math, b.Ci, 0, false, b.Co);
         b.tc_c2 = use_tc_conv(math, b.Co, b.Ci, res_slices, b.Co);
         c1.ep.gelu = 1; c1.ep.out = b.a1; c1.ep.out_pre = tr ? b.z1 : nullptr; c1.ep.round_tf32 = rnd && b.tc_c2;
+        c1.ep.fast_math = rnd;
         c1.w_blocked = b.tc_c1 && pl->blocked_weights;
         if (b.tc_c1) SINDDM_TRY(tc_conv_prepare(c1, &b.c1));
 

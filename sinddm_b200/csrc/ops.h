@@ -30,6 +30,7 @@ struct ConvEpilogue {
     float* out_final;       // ... written NCHW [B,3,H,W]; all null when unused
     int round_tf32;         // round `out` to tf32 (its only consumers are tensor-core operands)
     float* out;             // [P,N], or null when only out_final is wanted
+    int fast_math;          // CUDA-core kernels: use the TF32-mode GELU (gelu_fast) instead of erff (set with math = tf32)
 };
 
 struct ConvProblem {

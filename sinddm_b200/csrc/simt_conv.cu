@@ -186,8 +186,17 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int nspli
     const int total = ntaps * Cx * Cy;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
+    // eight loads in flight per thread; the additions keep the split order (deterministic)
     float s = 0.f;
-    for (int k = 0; k < nsplit; ++k) s += partial[(size_t)k * total + i];
+    int k = 0;
+    for (; k + 8 <= nsplit; k += 8) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __ldcs(partial + (size_t)(k + j) * total + i);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += v[j];
+    }
+    for (; k < nsplit; ++k) s += __ldcs(partial + (size_t)k * total + i);
     if (keep_layout) {
         dst[i] = s;
     } else {
@@ -400,50 +409,241 @@ simt_conv_smalln_kernel(const ConvProblem p) {
     for (int n = 0; n < N; ++n) conv_epilogue_one(p.ep, acc[n], n, N, (size_t)pix, x3v, fin);
 }
 
-// weight gradient with K = ntaps*Cx <= 32 accumulators per thread: dy is read ONCE for all taps.
-// grid = nsplit, block = (Cy padded to 32, kPY)
-template <int NTAPS, int CX>
-__global__ void simt_wgrad_smallcx_kernel(const WgradProblem p) {
-    constexpr int K = NTAPS * CX;
+// Cin == 3, N % 4 == 0 (l1.net[0]; the data gradient of final_conv): thread <-> (pixel pair, 4 output channels).
+// Consecutive threads own consecutive channel quads of one pixel pair, so every float4 store of a warp is
+// contiguous NHWC memory (the per-pixel kernel above scatters each store instruction over 32 cache lines), and
+// the quad's 4 x NTAPS*3 weights live in registers because the quad of a thread never changes.
+template <int NTAPS>
+__global__ void __launch_bounds__(256) simt_conv_cin3_kernel(const ConvProblem p, int n4, int ppb) {
+    constexpr int K = NTAPS * 3;
+    constexpr int R = NTAPS == 9 ? 3 : 1;      // window rows
+    constexpr int CW = NTAPS == 9 ? 4 : 2;     // window columns of a pixel pair
+    const int N = p.N;
+    const int quad = threadIdx.x % n4, pl = threadIdx.x / n4;
+    const int n0 = quad * 4;
+    const ConvEpilogue& ep = p.ep;
+    float wr[K][4];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) wr[k][j] = p.w[((size_t)(k / 3) * N + n0 + j) * 3 + (k % 3)];
+    }
+    float bias4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bias4[j] = ep.bias ? ep.bias[n0 + j] : 0.f;
+
+    const int wp = (p.W + 1) >> 1;                       // pixel pairs per row
+    const long long npairs = (long long)p.B * p.H * wp;
+    for (long long pg = blockIdx.x; pg * ppb < npairs; pg += gridDim.x) {
+        const long long pp = pg * ppb + pl;
+        if (pp >= npairs) continue;
+        const int w = (int)(pp % wp) * 2;
+        const long long row = pp / wp;                   // b * H + h
+        const int h = (int)(row % p.H);
+        // window of x: rows h-1..h+1, columns w-1..w+2 (3x3) or row h, columns w..w+1 (1x1)
+        float xw[R][CW][3];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int hh = h + (NTAPS == 9 ? r - 1 : 0);
+            const bool rok = hh >= 0 && hh < p.H;
+            const float* xrow = p.in + (row + (NTAPS == 9 ? r - 1 : 0)) * p.W * 3;
+#pragma unroll
+            for (int c = 0; c < CW; ++c) {
+                const int ww = w + (NTAPS == 9 ? c - 1 : c);
+                const bool ok = rok && ww >= 0 && ww < p.W;
+#pragma unroll
+                for (int ci = 0; ci < 3; ++ci) xw[r][c][ci] = ok ? __ldg(xrow + (size_t)ww * 3 + ci) : 0.f;
+            }
+        }
+#pragma unroll
+        for (int px = 0; px < 2; ++px) {
+            if (w + px >= p.W) break;
+            float v[4] = {bias4[0], bias4[1], bias4[2], bias4[3]};
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+#pragma unroll
+                for (int c = 0; c < (NTAPS == 9 ? 3 : 1); ++c) {
+#pragma unroll
+                    for (int ci = 0; ci < 3; ++ci) {
+                        const float xv = xw[r][c + px][ci];
+                        const int k = (r * (NTAPS == 9 ? 3 : 1) + c) * 3 + ci;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) v[j] = fmaf(xv, wr[k][j], v[j]);
+                    }
+                }
+            }
+            const size_t off = (size_t)(row * p.W + w + px) * N + n0;
+            if (ep.res_add) {
+                const float4 r4 = __ldg(reinterpret_cast<const float4*>(ep.res_add + off));
+                v[0] += r4.x; v[1] += r4.y; v[2] += r4.z; v[3] += r4.w;
+            }
+            if (ep.out_pre) __stcs(reinterpret_cast<float4*>(ep.out_pre + off), make_float4(v[0], v[1], v[2], v[3]));
+            if (ep.gelu) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] = ep.fast_math ? gelu_fast(v[j]) : gelu_erf(v[j]);
+            }
+            if (ep.dgelu_z) {
+                const float4 z = __ldg(reinterpret_cast<const float4*>(ep.dgelu_z + off));
+                const float zz[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] *= ep.fast_math ? gelu_grad_fast(zz[j]) : gelu_erf_grad(zz[j]);
+            }
+            if (ep.out) {
+                if (ep.round_tf32) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) v[j] = round_tf32(v[j]);
+                }
+                *reinterpret_cast<float4*>(ep.out + off) = make_float4(v[0], v[1], v[2], v[3]);
+            }
+        }
+    }
+}
+
+// N <= 3, Cin % 4 == 0, Cin <= 128 (the data gradient into l1's 3-channel depthwise output): one WARP per pixel,
+// lane j owns input channels 4j..4j+3, so a tap is one contiguous float4 load per lane (the per-pixel kernel above
+// strides every load instruction over 32 pixels) and the lane's 3 x NTAPS x 4 weights stay in registers; the three
+// sums are combined with shuffles.  A block is a strip of 12 pixels walking down the image: the rows it re-reads
+// for the vertical taps are still in L1.
+constexpr int kN3Warps = 12;
+
+template <int NTAPS>
+__global__ void __launch_bounds__(kN3Warps * 32, 1) simt_conv_n3_kernel(const ConvProblem p, int nstrips, int hsplit) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int C = p.Cin, N = p.N;
+    const bool lact = lane * 4 < C;
+    float wr[NTAPS][3][4];
+#pragma unroll
+    for (int t = 0; t < NTAPS; ++t) {
+#pragma unroll
+        for (int n = 0; n < 3; ++n) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                wr[t][n][j] = (lact && n < N) ? p.w[((size_t)t * N + n) * C + lane * 4 + j] : 0.f;
+        }
+    }
+    int bid = blockIdx.x;
+    const int part = bid % hsplit;
+    bid /= hsplit;
+    const int strip = bid % nstrips;
+    const int b = bid / nstrips;
+    const int w = strip * kN3Warps + warp;
+    if (w >= p.W) return;
+    const int h_begin = (int)((long long)p.H * part / hsplit), h_end = (int)((long long)p.H * (part + 1) / hsplit);
+    for (int h = h_begin; h < h_end; ++h) {
+        const size_t pix = ((size_t)b * p.H + h) * p.W + w;
+        float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int t = 0; t < NTAPS; ++t) {
+            const int hh = h + (NTAPS == 9 ? t / 3 - 1 : 0), ww = w + (NTAPS == 9 ? t % 3 - 1 : 0);
+            if (hh < 0 || hh >= p.H || ww < 0 || ww >= p.W || !lact) continue;
+            const float4 xv = __ldg(reinterpret_cast<const float4*>(
+                                        p.in + (((size_t)b * p.H + hh) * p.W + ww) * C) + lane);
+#pragma unroll
+            for (int n = 0; n < 3; ++n)
+                acc[n] = fmaf(xv.w, wr[t][n][3], fmaf(xv.z, wr[t][n][2], fmaf(xv.y, wr[t][n][1], fmaf(xv.x, wr[t][n][0], acc[n]))));
+        }
+#pragma unroll
+        for (int n = 0; n < 3; ++n) acc[n] = warp_sum(acc[n]);
+        if (lane == 0) {
+            float x3v[3] = {0.f, 0.f, 0.f};
+            float fin[3] = {0.f, 0.f, 0.f};
+            for (int n = 0; n < N; ++n) conv_epilogue_one(p.ep, acc[n], n, N, pix, x3v, fin);
+        }
+    }
+}
+
+// Weight gradient for Cx == 3 (l1.net[0], l1.res_conv, final_conv): dy is read ONCE for all taps.
+// One thread per output channel co walks row segments pixel by pixel; the 3x3 window of the three x channels
+// lives in registers and slides (9 new broadcast loads per pixel instead of 27), dy is prefetched one block of
+// six pixels ahead.  grid = nsplit CTAs of (Cy padded to 32, kPY) threads; walkers take (row, segment) items
+// round robin; partial[split][tap][ci][co] like the other weight-gradient kernels.
+constexpr int kCx3Block = 6;    // pixels per unrolled block = two rotations of the three window columns
+constexpr int kCx3Seg = 66;     // pixels per row segment (multiple of kCx3Block)
+
+template <int NTAPS>
+__global__ void __launch_bounds__(384, 2) simt_wgrad_cx3_kernel(const WgradProblem p, int seg_len, int nseg) {
+    constexpr int K = NTAPS * 3;
+    constexpr int R = NTAPS == 9 ? 3 : 1;      // window rows
     extern __shared__ float red[];  // [kPY][K][blockDim.x]
-    const int split = blockIdx.x;
     const int co = threadIdx.x, py = threadIdx.y;
-    const long long P = (long long)p.B * p.H * p.W;
-    const long long p_begin = P * split / p.nsplit;
-    const long long p_end = P * (split + 1) / p.nsplit;
     const bool act = co < p.Cy;
     float acc[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) acc[k] = 0.f;
-    // 4 pixels per iteration: their dy / x loads are independent and issue back to back (the per-pixel loop was
-    // bound by one L2 round trip per iteration)
-    constexpr int U = 4;
-    for (long long q0 = p_begin + py; q0 < p_end; q0 += (long long)kPY * U) {
-        if (!act) continue;
-        float g[U];
+
+    const int items = p.B * p.H * nseg;
+    const int nwalk = gridDim.x * kPY;
+    for (int item = blockIdx.x * kPY + py; item < items && act; item += nwalk) {
+        const int row = item / nseg, seg = item - row * nseg;
+        const int h = row % p.H;
+        const int w_begin = seg * seg_len;
+        const int w_end = min(p.W, w_begin + seg_len);
+        const float* dyrow = p.dy + (size_t)row * p.W * p.Cy + co;
+        const float* xrow[R];
+        bool rok[R];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const long long q = q0 + (long long)u * kPY;
-            g[u] = q < p_end ? __ldg(p.dy + q * p.Cy + co) : 0.f;
+        for (int r = 0; r < R; ++r) {
+            const int hh = h + (NTAPS == 9 ? r - 1 : 0);
+            rok[r] = hh >= 0 && hh < p.H;
+            xrow[r] = p.x + ((size_t)row + (NTAPS == 9 ? r - 1 : 0)) * p.W * 3;
         }
+        auto load_col = [&](float (&c)[R][3], int w) {
+            const bool wok = w >= 0 && w < p.W;
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const long long q = q0 + (long long)u * kPY;
-            if (q >= p_end) continue;
-            const int w = (int)(q % p.W);
-            const int h = (int)((q / p.W) % p.H);
+            for (int r = 0; r < R; ++r) {
 #pragma unroll
-            for (int tap = 0; tap < NTAPS; ++tap) {
-                int dyo = 0, dxo = 0;
-                if (NTAPS == 9) {
-                    dyo = tap / 3 - 1;
-                    dxo = tap % 3 - 1;
+                for (int ci = 0; ci < 3; ++ci) c[r][ci] = (wok && rok[r]) ? __ldg(xrow[r] + (size_t)w * 3 + ci) : 0.f;
+            }
+        };
+        auto load_g = [&](float (&g)[kCx3Block], int w) {
+#pragma unroll
+            for (int u = 0; u < kCx3Block; ++u) g[u] = (w + u < w_end) ? __ldg(dyrow + (size_t)(w + u) * p.Cy) : 0.f;
+        };
+        if (NTAPS == 9) {
+            float c0[R][3], c1[R][3], c2[R][3];
+            load_col(c0, w_begin - 1);
+            load_col(c1, w_begin);
+            // columns ca / cb / cc are at w-1 / w / w+1; the right one is fetched here
+            auto step = [&](float (&ca)[R][3], float (&cb)[R][3], float (&cc)[R][3], int w, float g) {
+                load_col(cc, w + 1);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+#pragma unroll
+                    for (int ci = 0; ci < 3; ++ci) {
+                        acc[(r * 3 + 0) * 3 + ci] = fmaf(ca[r][ci], g, acc[(r * 3 + 0) * 3 + ci]);
+                        acc[(r * 3 + 1) * 3 + ci] = fmaf(cb[r][ci], g, acc[(r * 3 + 1) * 3 + ci]);
+                        acc[(r * 3 + 2) * 3 + ci] = fmaf(cc[r][ci], g, acc[(r * 3 + 2) * 3 + ci]);
+                    }
                 }
-                const int hh = h + dyo, ww = w + dxo;
-                if (hh < 0 || hh >= p.H || ww < 0 || ww >= p.W) continue;
-                const float* xs = p.x + (q + (long long)dyo * p.W + dxo) * CX;
+            };
+            // no software prefetch here: 27 FMAs per pixel and 24 resident warps cover the dy latency
+            for (int w = w_begin; w < w_end; w += kCx3Block) {
+                float g[kCx3Block];
+                load_g(g, w);
+                step(c0, c1, c2, w + 0, g[0]);
+                step(c1, c2, c0, w + 1, g[1]);
+                step(c2, c0, c1, w + 2, g[2]);
+                step(c0, c1, c2, w + 3, g[3]);
+                step(c1, c2, c0, w + 4, g[4]);
+                step(c2, c0, c1, w + 5, g[5]);
+            }
+        } else {
+            float gn[kCx3Block];
+            load_g(gn, w_begin);
+            for (int w = w_begin; w < w_end; w += kCx3Block) {
+                float g[kCx3Block];
+                float c[kCx3Block][R][3];
 #pragma unroll
-                for (int ci = 0; ci < CX; ++ci) acc[tap * CX + ci] = fmaf(__ldg(xs + ci), g[u], acc[tap * CX + ci]);
+                for (int u = 0; u < kCx3Block; ++u) {
+                    g[u] = gn[u];
+                    load_col(c[u], w + u);
+                }
+                load_g(gn, w + kCx3Block);
+#pragma unroll
+                for (int u = 0; u < kCx3Block; ++u) {
+#pragma unroll
+                    for (int ci = 0; ci < 3; ++ci) acc[ci] = fmaf(c[u][0][ci], g[u], acc[ci]);
+                }
             }
         }
     }
@@ -456,8 +656,8 @@ __global__ void simt_wgrad_smallcx_kernel(const WgradProblem p) {
             float s = 0.f;
 #pragma unroll
             for (int y = 0; y < kPY; ++y) s += red[(y * K + k) * blockDim.x + co];
-            // k = tap*CX + ci  ->  partial[split][tap][ci][co]
-            p.partial[((size_t)split * K + k) * p.Cy + co] = s;
+            // k = tap*3 + ci  ->  partial[split][tap][ci][co]
+            p.partial[((size_t)blockIdx.x * K + k) * p.Cy + co] = s;
         }
     }
 }
@@ -468,6 +668,31 @@ int simt_conv_launch(const ConvProblem& p, cudaStream_t stream) {
     SINDDM_REQUIRE(p.ntaps == 9 || p.ntaps == 1, "simt_conv: ntaps must be 9 or 1");
     SINDDM_REQUIRE(p.N >= 1 && p.Cin >= 1, "simt_conv: bad channel counts");
     const long long P = (long long)p.B * p.H * p.W;
+    if (p.Cin == 3 && p.in_res == nullptr && p.N % 4 == 0 && p.N <= 512 && !p.ep.x3 && !p.ep.w_final) {
+        const int n4 = p.N / 4;
+        const int ppb = n4 >= 256 ? 1 : 256 / n4;
+        const long long npairs = (long long)p.B * p.H * ((p.W + 1) / 2);
+        const long long want = (npairs + ppb - 1) / ppb;
+        const long long cap = (long long)(device_info().initialized ? device_info().num_sms : 148) * 8;
+        const unsigned blocks = (unsigned)(want < cap ? want : cap);
+        if (p.ntaps == 9)
+            simt_conv_cin3_kernel<9><<<blocks, n4 * ppb, 0, stream>>>(p, n4, ppb);
+        else
+            simt_conv_cin3_kernel<1><<<blocks, n4 * ppb, 0, stream>>>(p, n4, ppb);
+        SINDDM_CUDA_OK(cudaGetLastError());
+        return SINDDM_OK;
+    }
+    if (p.N <= 3 && p.Cin % 4 == 0 && p.Cin <= 128 && p.in_res == nullptr && !p.ep.w_final && !p.ep.x3) {
+        const int nstrips = ceil_div(p.W, kN3Warps);
+        const int hsplit = p.H >= 32 ? 2 : 1;
+        const unsigned blocks = (unsigned)(p.B * nstrips * hsplit);
+        if (p.ntaps == 9)
+            simt_conv_n3_kernel<9><<<blocks, kN3Warps * 32, 0, stream>>>(p, nstrips, hsplit);
+        else
+            simt_conv_n3_kernel<1><<<blocks, kN3Warps * 32, 0, stream>>>(p, nstrips, hsplit);
+        SINDDM_CUDA_OK(cudaGetLastError());
+        return SINDDM_OK;
+    }
     if (p.Cin == 3 && p.in_res == nullptr && p.N <= 512) {
         const size_t smem = (size_t)p.ntaps * 3 * ((p.N + 3) & ~3) * sizeof(float);
         const unsigned blocks = (unsigned)((P + 127) / 128);
@@ -499,6 +724,9 @@ int simt_wgrad_nsplit(int B, int H, int W, int Cx, int Cy, int ntaps) {
     if (n > 1024) n = 1024;
     // keep the split-partial scratch of one layer under 64 MiB
     while (n > 1 && n * ntaps * Cx * Cy * 4 > (64ll << 20)) n /= 2;
+    // the Cx == 3 row walker wants two resident CTAs per SM and a short split reduction
+    const long long sms = device_info().initialized ? device_info().num_sms : 148;
+    if (Cx == 3 && n > 2 * sms) n = 2 * sms;
     return (int)n;
 }
 
@@ -507,12 +735,14 @@ int simt_wgrad_launch(const WgradProblem& p, cudaStream_t stream) {
     const int tx = (int)align_up((size_t)p.Cy, 32);
     SINDDM_REQUIRE(tx * kPY <= 1024, "simt_wgrad: Cy=%d too large", p.Cy);
     dim3 block(tx, kPY);
-    if (p.Cx == 3 && (size_t)kPY * p.ntaps * 3 * tx * sizeof(float) <= 48 * 1024) {
+    if (p.Cx == 3 && tx * kPY <= 384 && (size_t)kPY * p.ntaps * 3 * tx * sizeof(float) <= 48 * 1024) {
         const size_t smem = (size_t)kPY * p.ntaps * 3 * tx * sizeof(float);
+        const int seg_len = p.W > kCx3Seg ? kCx3Seg : ceil_div(p.W, kCx3Block) * kCx3Block;
+        const int nseg = ceil_div(p.W, seg_len);
         if (p.ntaps == 9)
-            simt_wgrad_smallcx_kernel<9, 3><<<p.nsplit, block, smem, stream>>>(p);
+            simt_wgrad_cx3_kernel<9><<<p.nsplit, block, smem, stream>>>(p, seg_len, nseg);
         else
-            simt_wgrad_smallcx_kernel<1, 3><<<p.nsplit, block, smem, stream>>>(p);
+            simt_wgrad_cx3_kernel<1><<<p.nsplit, block, smem, stream>>>(p, seg_len, nseg);
         SINDDM_CUDA_OK(cudaGetLastError());
         return SINDDM_OK;
     }
