@@ -177,112 +177,92 @@ __global__ void dw5x5_wgrad_final_kernel(const float* __restrict__ scratch, floa
 }
 
 // ---------------------------------------------------------------------------------------------------
-// TMA-staged versions (C % 4 == 0): the (8+4) x (32+4) pixel x 32 channel halo tile is brought into shared
-// memory by ONE bulk-tensor copy whose out-of-image part TMA zero-fills (= the conv's zero padding, no
-// bounds code at all); thread (channel, row) then slides its 5x5 window along the 32 columns reading
-// 5 shared-memory words per output (a warp = 32 channels of one pixel = one conflict-free 128-byte row).
+// TMA-staged versions (C % 4 == 0).  These kernels are bound by instruction issue long before HBM (25 FMAs per
+// output plus whatever surrounds them), so the layout of the work is chosen to minimise instructions per output:
+//   * tile = 16 x 16 output pixels x 32 channels; its (16+4) x (16+4) halo box is ONE bulk-tensor copy whose
+//     out-of-image part TMA zero-fills (= the conv's zero padding: no bounds code on the input side at all);
+//   * thread (channel lane, row pair ry) produces output rows 2ry and 2ry+1 together and slides a 6 x 5 register
+//     window along the 16 columns: 6 conflict-free shared-memory words (a warp = 32 channels of one pixel = one
+//     128-byte row) feed 50 FMAs in two independent chains -- 3 loads per output instead of 5;
+//   * a CTA walks up to kMaxTilesPerCta tiles of one tile row with a two-buffer TMA pipeline (the box of tile
+//     i+1 is in flight while tile i is computed), so the 25 weights / bias / condition are loaded once per CTA
+//     and two resident CTAs keep ~100 KB of loads in flight per SM;
+//   * interior tiles run a store path without any bounds predicate; the epilogue flavour (residual add, tf32
+//     rounding) is a template parameter.
 // ---------------------------------------------------------------------------------------------------
-constexpr int kTW = 32;                                  // output columns per tile
-constexpr int kTH = 8;                                   // output rows per tile (= threadIdx.y)
+constexpr int kTW = 16;                                  // output columns per tile
+constexpr int kTH = 16;                                  // output rows per tile (two per thread row)
 constexpr int kTileCols = kTW + 4, kTileRows = kTH + 4;
-constexpr int kTileFloats = kTileRows * kTileCols * 32;  // 13824 floats = 55296 B
+constexpr int kTileFloats = kTileRows * kTileCols * 32;  // 12800 floats = 51200 B
+constexpr int kRowThreads = kTH / 2;                     // threadIdx.y extent
+constexpr int kMaxTilesPerCta = 8;
 
-template <typename Body>
-SINDDM_DEVINL void slide_smem(const float* tile, int ry, int lane, Body&& body) {
-    // win[ky][slot], slot = tile column modulo 5
-    float win[5][5];
-    const float* base = tile + (size_t)ry * kTileCols * 32 + lane;
+// loads window column `col` (tile coordinates) of the six rows 2ry .. 2ry+5 into slot col % 5
+SINDDM_DEVINL void load_window_column(float (&win)[6][5], const float* base, int col) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int k = 0; k < 6; ++k) win[k][col % 5] = base[(k * kTileCols + col) * 32];
+}
+
+template <bool ADD, bool ROUND, bool FULL>
+SINDDM_DEVINL void dw5x5_tile(const float* tile, int ry, int lane, const float (&wr)[5][5], float bv, float cv,
+                              const float* __restrict__ addp, float* __restrict__ outp, size_t off, int C,
+                              size_t rowstride, int wvalid, bool ok_a, bool ok_b) {
+    // residual operand of the whole tile: 32 independent loads in flight before the first FMA needs one
+    float ad_a[kTW], ad_b[kTW];
+    if (ADD) {
 #pragma unroll
-        for (int ky = 0; ky < 5; ++ky) win[ky][j] = base[(ky * kTileCols + j) * 32];
-#pragma unroll   // fully unrolled: `wo` is a compile-time constant for the caller (register arrays indexed by it)
-    for (int w = 0; w < kTW; w += 5) {
+        for (int wo = 0; wo < kTW; ++wo) {
+            const size_t o = off + (size_t)wo * C;
+            ad_a[wo] = (FULL || (ok_a && wo < wvalid)) ? __ldg(addp + o) : 0.f;
+            ad_b[wo] = (FULL || (ok_b && wo < wvalid)) ? __ldg(addp + o + rowstride) : 0.f;
+        }
+    }
+    const float* base = tile + (size_t)(2 * ry) * kTileCols * 32 + lane;
+    float win[6][5];
 #pragma unroll
-        for (int j = 0; j < 5; ++j) {
-            const int wo = w + j;
-            if (wo < kTW) {
+    for (int j = 0; j < 4; ++j) load_window_column(win, base, j);
 #pragma unroll
-                for (int ky = 0; ky < 5; ++ky) win[ky][(j + 4) % 5] = base[(ky * kTileCols + wo + 4) * 32];
-                float x[5][5];
+    for (int wo = 0; wo < kTW; ++wo) {
+        load_window_column(win, base, wo + 4);
+        float acc_a = 0.f, acc_b = 0.f;
 #pragma unroll
-                for (int ky = 0; ky < 5; ++ky)
+        for (int ky = 0; ky < 5; ++ky) {
 #pragma unroll
-                    for (int kx = 0; kx < 5; ++kx) x[ky][kx] = win[ky][(j + kx) % 5];
-                body(wo, x);
+            for (int kx = 0; kx < 5; ++kx) {
+                acc_a = fmaf(win[ky][(wo + kx) % 5], wr[ky][kx], acc_a);
+                acc_b = fmaf(win[ky + 1][(wo + kx) % 5], wr[ky][kx], acc_b);
             }
         }
+        float va = (acc_a + bv) + cv;            // reference order: (conv + bias) + condition
+        float vb = (acc_b + bv) + cv;
+        if (ADD) {
+            va += ad_a[wo];
+            vb += ad_b[wo];
+        }
+        if (ROUND) {
+            va = round_tf32(va);
+            vb = round_tf32(vb);
+        }
+        const size_t o = off + (size_t)wo * C;
+        if (FULL || (ok_a && wo < wvalid)) outp[o] = va;
+        if (FULL || (ok_b && wo < wvalid)) outp[o + rowstride] = vb;
     }
 }
 
-__global__ void __launch_bounds__(256)
+template <bool ADD, bool ROUND>
+__global__ void __launch_bounds__(32 * kRowThreads, 2)
 dw5x5_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ wgt,
                  const float* __restrict__ bias, const float* __restrict__ cond, const float* __restrict__ add,
-                 float* __restrict__ out, int H, int W, int C, int tiles_w, int flip, int round) {
+                 float* __restrict__ out, int H, int W, int C, int tiles_w, int ncg, int tpc, int flip) {
     extern __shared__ __align__(128) uint8_t dsm[];
-    float* tile = reinterpret_cast<float*>(dsm);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(dsm + kTileFloats * sizeof(float));
-    const int lane = threadIdx.x, ry = threadIdx.y;
-    const int tw = blockIdx.x % tiles_w;
-    const int cg = blockIdx.x / tiles_w;
-    const int th = blockIdx.y, b = blockIdx.z;
-    const int tid = ry * 32 + lane;
-    if (tid == 0) {
-        mbar_init(bar, 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-    if (tid == 0) {
-        mbar_arrive_expect_tx(bar, kTileFloats * sizeof(float));
-        tma_load_4d(tile, &tm_in, bar, cg * 32, tw * kTW - 2, th * kTH - 2, b);
-    }
-    const int c = cg * 32 + lane;
-    const int h = th * kTH + ry;
-    const bool cok = c < C;
-    float wr[5][5];
-#pragma unroll
-    for (int t = 0; t < 25; ++t) wr[t / 5][t % 5] = cok ? __ldg(wgt + c * 25 + (flip ? 24 - t : t)) : 0.f;
-    const float bv = (bias && cok) ? __ldg(bias + c) : 0.f;
-    const float cv = (cond && cok) ? __ldg(cond + (size_t)b * C + c) : 0.f;
-    mbar_wait(bar, 0);
-    if (!cok || h >= H) return;
-    const size_t rowoff = (((size_t)b * H + h) * W) * C + c;
-    const int w0 = tw * kTW;
-    slide_smem(tile, ry, lane, [&](int wo, const float (&x)[5][5]) {
-        const int w = w0 + wo;
-        if (w < W) {
-            float acc = 0.f;
-#pragma unroll
-            for (int ky = 0; ky < 5; ++ky)
-#pragma unroll
-                for (int kx = 0; kx < 5; ++kx) acc = fmaf(x[ky][kx], wr[ky][kx], acc);
-            const size_t off = rowoff + (size_t)w * C;
-            float v = (acc + bv) + cv;           // reference order: (conv + bias) + condition
-            if (add) v += __ldg(add + off);
-            if (round) v = round_tf32(v);
-            out[off] = v;
-        }
-    });
-}
-
-// (A two-channels-per-thread variant with 64-channel boxes and packed fp32x2 FMAs was measured slower --
-// 1.03 ms vs 0.76 ms per 160-channel launch at 32x186x248 -- because its 125 registers halve the resident
-// warps; the one-channel kernel above stays.)
-
-// grid = (channel groups, row chunks, B); the CTA walks the column tiles of its 8-row chunk with a
-// double-buffered TMA pipeline and keeps the 26 sums per (channel, row) in registers.
-__global__ void __launch_bounds__(256)
-dw5x5_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __restrict__ dh,
-                       float* __restrict__ scratch, int H, int W, int C, int tiles_w, int nchunk) {
-    extern __shared__ __align__(128) uint8_t dsm[];
-    float* tiles = reinterpret_cast<float*>(dsm);   // 2 buffers; reused for the final reduction
+    float* tiles = reinterpret_cast<float*>(dsm);   // two halo boxes
     uint64_t* bar = reinterpret_cast<uint64_t*>(dsm + 2 * kTileFloats * sizeof(float));
     const int lane = threadIdx.x, ry = threadIdx.y;
-    const int cg = blockIdx.x, chunk = blockIdx.y, b = blockIdx.z;
+    const int cg = blockIdx.x % ncg, seg = blockIdx.x / ncg;
+    const int th = blockIdx.y, b = blockIdx.z;
     const int tid = ry * 32 + lane;
-    const int c = cg * 32 + lane;
-    const int h = chunk * kTH + ry;
-    const bool active = c < C && h < H;
+    const int tw0 = seg * tpc;
+    const int ntile = min(tpc, tiles_w - tw0);
     if (tid == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
@@ -291,57 +271,131 @@ dw5x5_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __
     __syncthreads();
     if (tid == 0) {
         mbar_arrive_expect_tx(&bar[0], kTileFloats * sizeof(float));
-        tma_load_4d(tiles, &tm_x, &bar[0], cg * 32, -2, chunk * kTH - 2, b);
+        tma_load_4d(tiles, &tm_in, &bar[0], cg * 32, tw0 * kTW - 2, th * kTH - 2, b);
+    }
+    const int c = cg * 32 + lane;
+    const bool cok = c < C;
+    const int cc = cok ? c : 0;
+    float wr[5][5];
+#pragma unroll
+    for (int t = 0; t < 25; ++t) wr[t / 5][t % 5] = __ldg(wgt + cc * 25 + (flip ? 24 - t : t));
+    const float bv = bias ? __ldg(bias + cc) : 0.f;
+    const float cv = cond ? __ldg(cond + (size_t)b * C + cc) : 0.f;
+    const int h = th * kTH + 2 * ry;
+    const bool ok_a = cok && h < H, ok_b = cok && h + 1 < H;
+    const bool rows_full = th * kTH + kTH <= H && cg * 32 + 32 <= C;   // CTA-uniform
+    const size_t rowstride = (size_t)W * C;
+    const size_t rowoff = ((size_t)b * H + (h < H ? h : 0)) * rowstride + cc;
+
+    for (int i = 0; i < ntile; ++i) {
+        const int buf = i & 1;
+        if (tid == 0 && i + 1 < ntile) {
+            // the other buffer was consumed in iteration i-1 (all threads passed the __syncthreads below)
+            mbar_arrive_expect_tx(&bar[buf ^ 1], kTileFloats * sizeof(float));
+            tma_load_4d(tiles + (size_t)(buf ^ 1) * kTileFloats, &tm_in, &bar[buf ^ 1], cg * 32,
+                        (tw0 + i + 1) * kTW - 2, th * kTH - 2, b);
+        }
+        const int w0 = (tw0 + i) * kTW;
+        const size_t off = rowoff + (size_t)w0 * C;
+        const float* tile = tiles + (size_t)buf * kTileFloats;
+        if (rows_full && w0 + kTW <= W) {
+            // (the residual operand loads are issued before the wait: they overlap the box's arrival)
+            mbar_wait(&bar[buf], (uint32_t)(i >> 1) & 1u);
+            dw5x5_tile<ADD, ROUND, true>(tile, ry, lane, wr, bv, cv, add, out, off, C, rowstride, kTW, true, true);
+        } else {
+            mbar_wait(&bar[buf], (uint32_t)(i >> 1) & 1u);
+            dw5x5_tile<ADD, ROUND, false>(tile, ry, lane, wr, bv, cv, add, out, off, C, rowstride, W - w0, ok_a, ok_b);
+        }
+        __syncthreads();   // everyone is done with `buf` before it is refilled
+    }
+}
+
+// Weight / bias / conditioning gradients with the same tiling: thread (channel, row pair) keeps the 25 tap sums
+// and the plain sum of its channel in registers while its CTA walks the tiles of (up to) half a tile row; the 32
+// upstream-gradient values of a tile are fetched together before the halo box is waited for.  Out-of-image pixels
+// contribute through a zero upstream gradient, so there is no bounds code in the FMA loop.
+// scratch[b][chunk = th * nseg + seg][26][C]
+__global__ void __launch_bounds__(32 * kRowThreads, 2)
+dw5x5_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __restrict__ dh,
+                       float* __restrict__ scratch, int H, int W, int C, int tiles_w, int ncg, int tpc, int nseg) {
+    extern __shared__ __align__(128) uint8_t dsm[];
+    float* tiles = reinterpret_cast<float*>(dsm);   // 2 buffers; reused for the final reduction
+    uint64_t* bar = reinterpret_cast<uint64_t*>(dsm + 2 * kTileFloats * sizeof(float));
+    const int lane = threadIdx.x, ry = threadIdx.y;
+    const int cg = blockIdx.x % ncg, seg = blockIdx.x / ncg;
+    const int th = blockIdx.y, b = blockIdx.z;
+    const int tid = ry * 32 + lane;
+    const int c = cg * 32 + lane;
+    const int h = th * kTH + 2 * ry;
+    const bool cok = c < C;
+    const bool ok_a = cok && h < H, ok_b = cok && h + 1 < H;
+    const int tw0 = seg * tpc;
+    const int ntile = min(tpc, tiles_w - tw0);
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_arrive_expect_tx(&bar[0], kTileFloats * sizeof(float));
+        tma_load_4d(tiles, &tm_x, &bar[0], cg * 32, tw0 * kTW - 2, th * kTH - 2, b);
     }
     float acc[5][5];
 #pragma unroll
     for (int t = 0; t < 25; ++t) acc[t / 5][t % 5] = 0.f;
     float gsum = 0.f;
-    const float* dhrow = dh + (((size_t)b * H + (h < H ? h : 0)) * W) * C + (c < C ? c : 0);
+    const size_t rowstride = (size_t)W * C;
+    const float* dhrow = dh + ((size_t)b * H + (h < H ? h : 0)) * rowstride + (cok ? c : 0);
 
-    for (int tw = 0; tw < tiles_w; ++tw) {
-        const int buf = tw & 1;
-        if (tid == 0 && tw + 1 < tiles_w) {
-            // the other buffer was consumed in iteration tw-1 (all threads passed the __syncthreads below)
+    for (int i = 0; i < ntile; ++i) {
+        const int buf = i & 1;
+        if (tid == 0 && i + 1 < ntile) {
             mbar_arrive_expect_tx(&bar[buf ^ 1], kTileFloats * sizeof(float));
-            tma_load_4d(tiles + (size_t)(buf ^ 1) * kTileFloats, &tm_x, &bar[buf ^ 1], cg * 32, (tw + 1) * kTW - 2,
-                        chunk * kTH - 2, b);
+            tma_load_4d(tiles + (size_t)(buf ^ 1) * kTileFloats, &tm_x, &bar[buf ^ 1], cg * 32,
+                        (tw0 + i + 1) * kTW - 2, th * kTH - 2, b);
         }
-        mbar_wait(&bar[buf], (uint32_t)(tw >> 1) & 1u);
-        if (active) {
-            const int w0 = tw * kTW;
-            // the 32 upstream-gradient values of this row segment: issued together (32 loads in flight) instead of
-            // one dependent load per pixel inside the sliding loop
-            float gv[kTW];
+        const int w0 = (tw0 + i) * kTW;
+        float g_a[kTW], g_b[kTW];
 #pragma unroll
-            for (int i = 0; i < kTW; ++i) gv[i] = (w0 + i < W) ? __ldg(dhrow + (size_t)(w0 + i) * C) : 0.f;
-            slide_smem(tiles + (size_t)buf * kTileFloats, ry, lane, [&](int wo, const float (&xv)[5][5]) {
-                const int w = w0 + wo;
-                if (w < W) {
-                    const float g = gv[wo];
-                    gsum += g;
+        for (int wo = 0; wo < kTW; ++wo) {
+            const size_t o = (size_t)(w0 + wo) * C;
+            g_a[wo] = (ok_a && w0 + wo < W) ? __ldg(dhrow + o) : 0.f;
+            g_b[wo] = (ok_b && w0 + wo < W) ? __ldg(dhrow + o + rowstride) : 0.f;
+        }
+        mbar_wait(&bar[buf], (uint32_t)(i >> 1) & 1u);
+        const float* base = tiles + (size_t)buf * kTileFloats + (size_t)(2 * ry) * kTileCols * 32 + lane;
+        float win[6][5];
 #pragma unroll
-                    for (int ky = 0; ky < 5; ++ky)
+        for (int j = 0; j < 4; ++j) load_window_column(win, base, j);
 #pragma unroll
-                        for (int kx = 0; kx < 5; ++kx) acc[ky][kx] = fmaf(xv[ky][kx], g, acc[ky][kx]);
-                }
-            });
+        for (int wo = 0; wo < kTW; ++wo) {
+            load_window_column(win, base, wo + 4);
+            const float ga = g_a[wo], gb = g_b[wo];
+            gsum += ga + gb;
+#pragma unroll
+            for (int ky = 0; ky < 5; ++ky) {
+#pragma unroll
+                for (int kx = 0; kx < 5; ++kx)
+                    acc[ky][kx] = fmaf(win[ky + 1][(wo + kx) % 5], gb, fmaf(win[ky][(wo + kx) % 5], ga, acc[ky][kx]));
+            }
         }
         __syncthreads();   // everyone is done with `buf` before it is refilled two iterations later
     }
-    // reduce over the 8 rows through shared memory (the tile buffers are free now)
+    // reduce over the 8 row pairs through shared memory (the tile buffers are free now)
     float* red = tiles;    // [8][26][32]
 #pragma unroll
-    for (int t = 0; t < 25; ++t) red[(ry * 26 + t) * 32 + lane] = active ? acc[t / 5][t % 5] : 0.f;
-    red[(ry * 26 + 25) * 32 + lane] = active ? gsum : 0.f;
+    for (int t = 0; t < 25; ++t) red[(ry * 26 + t) * 32 + lane] = acc[t / 5][t % 5];
+    red[(ry * 26 + 25) * 32 + lane] = gsum;
     __syncthreads();
-    for (int i = tid; i < 26 * 32; i += 256) {
+    const int chunk = th * nseg + seg, nchunk = gridDim.y * nseg;
+    for (int i = tid; i < 26 * 32; i += 32 * kRowThreads) {
         const int t = i / 32, l = i % 32;
         const int cc = cg * 32 + l;
         if (cc < C) {
             float s = 0.f;
 #pragma unroll
-            for (int y = 0; y < kTH; ++y) s += red[(y * 26 + t) * 32 + l];
+            for (int y = 0; y < kRowThreads; ++y) s += red[(y * 26 + t) * 32 + l];
             scratch[(((size_t)b * nchunk + chunk) * 26 + t) * C + cc] = s;
         }
     }
@@ -349,26 +403,46 @@ dw5x5_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __
 
 }  // namespace
 
+// tiles per CTA along a tile row: long walks amortise the per-CTA setup, but small images still need
+// a few CTAs per SM
+static int tiles_per_cta(int tiles_w, long long ctas_per_segment, int max_tpc) {
+    const long long want = 4ll * (device_info().initialized ? device_info().num_sms : 148);
+    int tpc = max_tpc < tiles_w ? max_tpc : tiles_w;
+    while (tpc > 1 && ctas_per_segment * ceil_div(tiles_w, tpc) < want) tpc = (tpc + 1) / 2;
+    return tpc;
+}
+
+template <bool ADD, bool ROUND>
+static int dw5x5_tma_launch(const CUtensorMap& tm, const float* w, const float* bias, const float* cond,
+                            const float* add, float* out, int B, int H, int W, int C, int flip, cudaStream_t stream) {
+    const size_t smem = 2 * kTileFloats * sizeof(float) + 16;
+    static int attr_set = 0;
+    if (!attr_set) {
+        SINDDM_CUDA_OK(cudaFuncSetAttribute(dw5x5_tma_kernel<ADD, ROUND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)smem));
+        attr_set = 1;
+    }
+    const int tiles_w = ceil_div(W, kTW), tiles_h = ceil_div(H, kTH), ncg = ceil_div(C, 32);
+    const int tpc = tiles_per_cta(tiles_w, (long long)ncg * tiles_h * B, kMaxTilesPerCta);
+    dim3 grid(ncg * ceil_div(tiles_w, tpc), tiles_h, B);
+    dim3 block(32, kRowThreads);
+    dw5x5_tma_kernel<ADD, ROUND><<<grid, block, smem, stream>>>(tm, w, bias, cond, add, out, H, W, C, tiles_w, ncg,
+                                                                 tpc, flip);
+    SINDDM_CUDA_OK(cudaGetLastError());
+    return SINDDM_OK;
+}
+
 int dw5x5_launch(const float* in, const float* w, const float* bias, const float* cond, const float* add, float* out,
                  int B, int H, int W, int C, int flip, int round_tf32, cudaStream_t stream) {
     SINDDM_REQUIRE(B <= 65535, "dw5x5: batch too large");
     if (C % 4 == 0 && device_info().initialized) {
         CUtensorMap tm;
         SINDDM_TRY(make_tmap_nhwc(&tm, in, B, H, W, C, 32, kTileCols, kTileRows, CU_TENSOR_MAP_SWIZZLE_NONE));
-        const int tiles_w = ceil_div(W, kTW);
-        const size_t smem = kTileFloats * sizeof(float) + 16;
-        static int attr_set = 0;
-        if (!attr_set) {
-            SINDDM_CUDA_OK(cudaFuncSetAttribute(dw5x5_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                (int)smem));
-            attr_set = 1;
-        }
-        dim3 grid(tiles_w * ceil_div(C, 32), ceil_div(H, kTH), B);
-        dim3 block(32, kTH);
-        dw5x5_tma_kernel<<<grid, block, smem, stream>>>(tm, w, bias, cond, add, out, H, W, C, tiles_w, flip,
-                                                        round_tf32);
-        SINDDM_CUDA_OK(cudaGetLastError());
-        return SINDDM_OK;
+        if (add)
+            return round_tf32 ? dw5x5_tma_launch<true, true>(tm, w, bias, cond, add, out, B, H, W, C, flip, stream)
+                              : dw5x5_tma_launch<true, false>(tm, w, bias, cond, add, out, B, H, W, C, flip, stream);
+        return round_tf32 ? dw5x5_tma_launch<false, true>(tm, w, bias, cond, add, out, B, H, W, C, flip, stream)
+                          : dw5x5_tma_launch<false, false>(tm, w, bias, cond, add, out, B, H, W, C, flip, stream);
     }
     const int nseg = ceil_div(W, kSeg);
     dim3 grid(nseg * ceil_div(C, 32), ceil_div(H, kRowsPerBlock), B);
@@ -378,17 +452,17 @@ int dw5x5_launch(const float* in, const float* w, const float* bias, const float
     return SINDDM_OK;
 }
 
+// both weight-gradient kernels write at most ceil(H/8) + 1 chunks of 26 x C partial sums per image: the CUDA-core
+// kernel one per 8 rows, the TMA kernel at most two (row halves) per 16 rows
 size_t dw5x5_wgrad_scratch_floats(int B, int H, int C) {
-    return (size_t)B * ceil_div(H, kRowsPerChunk) * 26 * C;
+    return (size_t)B * (ceil_div(H, kRowsPerChunk) + 1) * 26 * C;
 }
 
 int dw5x5_wgrad_launch(const float* x, const float* dh, float* dw, float* db, float* dcond, float* scratch, int B,
                        int H, int W, int C, cudaStream_t stream) {
     SINDDM_REQUIRE(B <= 65535, "dw5x5_wgrad: batch too large");
-    static_assert(kRowsPerChunk == kTH, "scratch layout assumes 8-row chunks in both kernels");
-    const int nchunk = ceil_div(H, kRowsPerChunk);
-    dim3 grid(ceil_div(C, 32), nchunk, B);
-    dim3 block(32, kRowsPerChunk);
+    static_assert(2 * kRowsPerChunk == kTH, "scratch bound assumes 8-row chunks vs 16-row tiles");
+    int nchunk;
     if (C % 4 == 0 && device_info().initialized) {
         CUtensorMap tm;
         SINDDM_TRY(make_tmap_nhwc(&tm, x, B, H, W, C, 32, kTileCols, kTileRows, CU_TENSOR_MAP_SWIZZLE_NONE));
@@ -399,8 +473,19 @@ int dw5x5_wgrad_launch(const float* x, const float* dh, float* dw, float* db, fl
                                                 (int)smem));
             attr_set = 1;
         }
-        dw5x5_wgrad_tma_kernel<<<grid, block, smem, stream>>>(tm, dh, scratch, H, W, C, ceil_div(W, kTW), nchunk);
+        const int tiles_w = ceil_div(W, kTW), tiles_h = ceil_div(H, kTH), ncg = ceil_div(C, 32);
+        // at most two segments per tile row (the scratch bound above)
+        int tpc = tiles_per_cta(tiles_w, (long long)ncg * tiles_h * B, tiles_w);
+        if (tpc < ceil_div(tiles_w, 2)) tpc = ceil_div(tiles_w, 2);
+        const int nseg = ceil_div(tiles_w, tpc);
+        nchunk = tiles_h * nseg;
+        dim3 grid(ncg * nseg, tiles_h, B);
+        dim3 block(32, kRowThreads);
+        dw5x5_wgrad_tma_kernel<<<grid, block, smem, stream>>>(tm, dh, scratch, H, W, C, tiles_w, ncg, tpc, nseg);
     } else {
+        nchunk = ceil_div(H, kRowsPerChunk);
+        dim3 grid(ceil_div(C, 32), nchunk, B);
+        dim3 block(32, kRowsPerChunk);
         dw5x5_wgrad_partial_kernel<<<grid, block, 0, stream>>>(x, dh, scratch, B, H, W, C, nchunk);
     }
     SINDDM_CUDA_OK(cudaGetLastError());

@@ -52,6 +52,12 @@ bool use_tc_conv(int math, int Cin, int Cres, bool has_res_slices, int N) {
     return tc_conv_supported(p);
 }
 
+// Rows of the first-conv data-gradient operand: a 3-channel result (l1) runs on the tensor cores with N padded to 16
+// zero weight rows (3 of 16 accumulator columns are stored) instead of a CUDA-core kernel.
+inline int d1_rows(int math, int Ci, int Co) {
+    return (Ci < 16 && use_tc_conv(math, Co, 0, false, 16)) ? 16 : Ci;
+}
+
 bool use_tc_wgrad(int math, int Cx, int Cy) { return math == MATH_TF32 && tc_wgrad_supported(Cx, Cy); }
 
 int wgrad_nsplit(int math, int B, int H, int W, int Cx, int Cy, int ntaps) {
@@ -91,7 +97,7 @@ size_t carve(Plan* pl, uint8_t* base) {
         b.w0_f = cv.take(packed_weight_floats(9, b.Co, b.Ci));
         b.w2_f = cv.take(packed_weight_floats(9, b.Co, b.Co));
         b.wr_f = b.has_res ? cv.take(packed_weight_floats(1, b.Co, b.Ci)) : nullptr;
-        b.w0_d = tr ? cv.take(packed_weight_floats(9, b.Ci, b.Co)) : nullptr;
+        b.w0_d = tr ? cv.take(packed_weight_floats(9, d1_rows(pl->math, b.Ci, b.Co), b.Co)) : nullptr;
         b.w2_d = tr ? cv.take(packed_weight_floats(9, b.Co, b.Co)) : nullptr;
         b.wr_d = (tr && b.has_res) ? cv.take(packed_weight_floats(1, b.Ci, b.Co)) : nullptr;
         b.bias2c = b.has_res ? cv.take((size_t)b.Co) : nullptr;
@@ -211,7 +217,8 @@ int plan_build(Plan* pl, int B, int H, int W, int dim, int channels, int math, i
         SINDDM_CUDA_OK(cudaMemset(b.w0_f, 0, packed_weight_floats(9, b.Co, b.Ci) * sizeof(float)));
         SINDDM_CUDA_OK(cudaMemset(b.w2_f, 0, packed_weight_floats(9, b.Co, b.Co) * sizeof(float)));
         if (b.wr_f) SINDDM_CUDA_OK(cudaMemset(b.wr_f, 0, packed_weight_floats(1, b.Co, b.Ci) * sizeof(float)));
-        if (b.w0_d) SINDDM_CUDA_OK(cudaMemset(b.w0_d, 0, packed_weight_floats(9, b.Ci, b.Co) * sizeof(float)));
+        if (b.w0_d)
+            SINDDM_CUDA_OK(cudaMemset(b.w0_d, 0, packed_weight_floats(9, d1_rows(math, b.Ci, b.Co), b.Co) * sizeof(float)));
         if (b.w2_d) SINDDM_CUDA_OK(cudaMemset(b.w2_d, 0, packed_weight_floats(9, b.Co, b.Co) * sizeof(float)));
         if (b.wr_d) SINDDM_CUDA_OK(cudaMemset(b.wr_d, 0, packed_weight_floats(1, b.Ci, b.Co) * sizeof(float)));
     }
@@ -262,9 +269,10 @@ int plan_build(Plan* pl, int B, int H, int W, int dim, int channels, int math, i
             ConvProblem& d1 = b.pd1;
             memset(&d1, 0, sizeof(d1));
             d1.B = B; d1.H = H; d1.W = W;
-            d1.in = pl->dz1; d1.Cin = b.Co; d1.w = b.w0_d; d1.ntaps = 9; d1.N = b.Ci;
-            d1.ep.out = pl->dh0;
-            b.tc_d1 = use_tc_conv(math, b.Co, 0, false, b.Ci);
+            d1.in = pl->dz1; d1.Cin = b.Co; d1.w = b.w0_d; d1.ntaps = 9; d1.N = d1_rows(math, b.Ci, b.Co);
+            if (d1.N != b.Ci) d1.ep.out3 = pl->dh0;     // padded tensor-core problem: columns 0..2 -> [P,3]
+            else d1.ep.out = pl->dh0;
+            b.tc_d1 = use_tc_conv(math, b.Co, 0, false, d1.N);
 
             ConvProblem& dr = b.pdr;
             memset(&dr, 0, sizeof(dr));
@@ -344,8 +352,16 @@ int net_pack_weights(Plan* pl, const float* const* params, cudaStream_t s) {
     for (int l = 0; l < kNumBlocks; ++l) {
         BlockBufs& b = pl->blk[l];
         // tensor-core layers read the blocked pre-swizzled layout, CUDA-core layers the plain [tap][N][K] one
-        SINDDM_TRY(pack_conv_weights_launch(params[b.pbase + 6], b.Co, b.Ci, 9, b.w0_f, b.w0_d, rnd && b.tc_c1, s,
-                                            b.tc_c1 && pl->blocked_weights));
+        if (pl->training && b.tc_d1 != b.tc_c1) {
+            // l1: the forward conv (Cin = 3) runs on CUDA cores, its data gradient on the tensor cores
+            SINDDM_TRY(pack_conv_weights_launch(params[b.pbase + 6], b.Co, b.Ci, 9, b.w0_f, nullptr, rnd && b.tc_c1, s,
+                                                b.tc_c1 && pl->blocked_weights));
+            SINDDM_TRY(pack_conv_weights_launch(params[b.pbase + 6], b.Co, b.Ci, 9, nullptr, b.w0_d, rnd && b.tc_d1, s,
+                                                b.tc_d1 && pl->blocked_weights, b.pd1.N));
+        } else {
+            SINDDM_TRY(pack_conv_weights_launch(params[b.pbase + 6], b.Co, b.Ci, 9, b.w0_f, b.w0_d, rnd && b.tc_c1, s,
+                                                b.tc_c1 && pl->blocked_weights, pl->training ? b.pd1.N : 0));
+        }
         SINDDM_TRY(pack_conv_weights_launch(params[b.pbase + 8], b.Co, b.Co, 9, b.w2_f, b.w2_d, rnd && b.tc_c2, s,
                                             b.tc_c2 && pl->blocked_weights));
         if (b.has_res) {

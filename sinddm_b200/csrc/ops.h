@@ -29,7 +29,9 @@ struct ConvEpilogue {
     const float* b_final;   // ... bias [3] ...
     float* out_final;       // ... written NCHW [B,3,H,W]; all null when unused
     int round_tf32;         // round `out` to tf32 (its only consumers are tensor-core operands)
-    float* out;             // [P,N], or null when only out_final is wanted
+    float* out;             // [P,N], or null when only out_final / out3 is wanted
+    float* out3;            // tensor-core path only: [P,3] NHWC copy of result columns 0..2 (a 3-channel result computed
+                            // with N padded to 16 zero weight rows), or null
     int fast_math;          // CUDA-core kernels: use the TF32-mode GELU (gelu_fast) instead of erff (set with math = tf32)
 };
 
@@ -103,8 +105,9 @@ int wgrad_reduce_launch(const float* partial, int nsplit, int ntaps, int Cx, int
 //   fwd : dst[tap][co][ci] = w[co][ci][tap]
 //   dgrad: dst[tap][ci][co] = w[co][ci][ntaps-1-tap]
 // ------------------------------------------------------------------------------------------------
+// dgrad_rows > Cin pads the data-gradient operand to that many rows (the extra rows are never written: clear them once).
 int pack_conv_weights_launch(const float* w, int Cout, int Cin, int ntaps, float* dst_fwd, float* dst_dgrad, int round,
-                             cudaStream_t stream, int blocked = 0);
+                             cudaStream_t stream, int blocked = 0, int dgrad_rows = 0);
 // floats needed by a packed weight buffer in either layout ([ntaps][N][K] or blocked with K padded to 32)
 inline size_t packed_weight_floats(int ntaps, int N, int K) { return (size_t)ntaps * N * ((K + 31) / 32 * 32); }
 

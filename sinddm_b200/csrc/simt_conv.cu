@@ -219,7 +219,7 @@ __device__ __forceinline__ size_t packed_index(int tap, int n, int k, int N, int
 
 __global__ void pack_conv_weights_kernel(const float* __restrict__ w, int Cout, int Cin, int ntaps,
                                          float* __restrict__ dst_fwd, float* __restrict__ dst_dgrad, int round,
-                                         int blocked) {
+                                         int blocked, int dgrad_rows) {
     const int total = Cout * Cin * ntaps;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
@@ -229,7 +229,7 @@ __global__ void pack_conv_weights_kernel(const float* __restrict__ w, int Cout, 
     float v = w[i];
     if (round) v = round_tf32(v);
     if (dst_fwd) dst_fwd[packed_index(tap, co, ci, Cout, Cin, blocked)] = v;
-    if (dst_dgrad) dst_dgrad[packed_index(ntaps - 1 - tap, ci, co, Cin, Cout, blocked)] = v;
+    if (dst_dgrad) dst_dgrad[packed_index(ntaps - 1 - tap, ci, co, dgrad_rows, Cout, blocked)] = v;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -760,10 +760,10 @@ int wgrad_reduce_launch(const float* partial, int nsplit, int ntaps, int Cx, int
 }
 
 int pack_conv_weights_launch(const float* w, int Cout, int Cin, int ntaps, float* dst_fwd, float* dst_dgrad, int round,
-                             cudaStream_t stream, int blocked) {
+                             cudaStream_t stream, int blocked, int dgrad_rows) {
     const int total = Cout * Cin * ntaps;
     pack_conv_weights_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(w, Cout, Cin, ntaps, dst_fwd, dst_dgrad, round,
-                                                                       blocked);
+                                                                       blocked, dgrad_rows > Cin ? dgrad_rows : Cin);
     SINDDM_CUDA_OK(cudaGetLastError());
     return SINDDM_OK;
 }

@@ -490,6 +490,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                             fin[2] = fmaf(v[j], s_wfinal[2 * N + cc + j], fin[2]);
                         }
                     }
+                    if (ep.out3 && cc == 0 && valid) {
+                        // a lane owns one pixel: the warp's 32 x 12 bytes are contiguous NHWC memory
+                        float* o3 = ep.out3 + pix * 3;
+                        o3[0] = v[0];
+                        o3[1] = v[1];
+                        o3[2] = v[2];
+                    }
                     if (ep.out && live) {
                         if (ep.round_tf32) {
 #pragma unroll
