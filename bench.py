@@ -294,10 +294,12 @@ def run_b200_arm(args):
     barrier()
     e2e_per_scale = [0.0] * 5
     t0 = time.perf_counter()
+    e2e_steps = []
     for i in range(args.steps):
         ts = time.perf_counter()
         e2e_step(i)
-        e2e_per_scale[i % 5] += time.perf_counter() - ts
+        e2e_steps.append(time.perf_counter() - ts)
+        e2e_per_scale[i % 5] += e2e_steps[-1]
     barrier()
     e2e_s = reduce_max(time.perf_counter() - t0)
     e2e_per_scale = [1e3 * v / max(1, len(range(k, args.steps, 5))) for k, v in enumerate(e2e_per_scale)]
@@ -309,13 +311,15 @@ def run_b200_arm(args):
     sample_once()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    l0 = lib.sinddm_launch_count()
+    import sinddm_b200.diffusion as sdiff
+    l0, g0 = lib.sinddm_launch_count(), sdiff.graph_replayed_launches
     e0.record()
     out = sample_once()
     e1.record()
     barrier()
     sample_ms = reduce_max(e0.elapsed_time(e1))
-    sample_launches = int(lib.sinddm_launch_count() - l0)
+    # kernels launched directly + kernels executed by CUDA-graph replays of the captured timestep
+    sample_launches = int(lib.sinddm_launch_count() - l0) + int(sdiff.graph_replayed_launches - g0)
     t0 = time.perf_counter()
     final = sample_once()[-1]
     host_imgs = final.cpu()                                   # images read back to the host
@@ -368,6 +372,7 @@ def run_b200_arm(args):
         "gpu_launches": launches,
         "per_scale_ms_per_step": per_scale,
         "e2e_per_scale_ms_per_step": e2e_per_scale,
+        "e2e_slowest_step": {"index": int(np.argmax(e2e_steps)), "ms": 1e3 * float(np.max(e2e_steps))},
         "finest_scale_steps_per_sec": 1e3 / per_scale[4] * world,
         "achieved_tflops_whole_step": TRAIN_FLOP_PER_PX * mean_px() * BATCH * steps_per_s / 1e12,
         "roofline": {"bound": "tensor", "kernel": "tc_conv_kernel (3x3/1x1 conv forward + data gradient)",

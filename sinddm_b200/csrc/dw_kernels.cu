@@ -177,6 +177,103 @@ __global__ void dw5x5_wgrad_final_kernel(const float* __restrict__ scratch, floa
 }
 
 // ---------------------------------------------------------------------------------------------------
+// C == 3 (l1.ds_conv on the network input): the channel-per-lane kernels above would leave 29 of 32 lanes idle.
+// Here a thread owns a PIXEL and all three channels: the 75 weights sit in registers, neighbouring threads read
+// neighbouring 12-byte pixels (every load instruction of a warp covers one contiguous 384-byte span, and the 25
+// taps of a pixel hit lines its neighbours already pulled into L1).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+dw5x5_c3_kernel(const float* __restrict__ in, const float* __restrict__ wgt, const float* __restrict__ bias,
+                const float* __restrict__ cond, const float* __restrict__ add, float* __restrict__ out, int B, int H,
+                int W, int flip, int round) {
+    float wr[25][3];
+#pragma unroll
+    for (int t = 0; t < 25; ++t)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) wr[t][c] = __ldg(wgt + c * 25 + (flip ? 24 - t : t));
+    const long long P = (long long)B * H * W;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+        const int w = (int)(p % W);
+        const int h = (int)((p / W) % H);
+        const int b = (int)(p / ((long long)W * H));
+        float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ky = 0; ky < 5; ++ky) {
+            const int hh = h + ky - 2;
+            if (hh < 0 || hh >= H) continue;
+            const float* row = in + (p + (long long)(ky - 2) * W) * 3;
+#pragma unroll
+            for (int kx = 0; kx < 5; ++kx) {
+                const int ww = w + kx - 2;
+                if (ww < 0 || ww >= W) continue;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) acc[c] = fmaf(__ldg(row + (kx - 2) * 3 + c), wr[ky * 5 + kx][c], acc[c]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float v = (acc[c] + (bias ? __ldg(bias + c) : 0.f)) + (cond ? __ldg(cond + b * 3 + c) : 0.f);
+            if (add) v += __ldg(add + p * 3 + c);
+            out[p * 3 + c] = round ? round_tf32(v) : v;
+        }
+    }
+}
+
+// gradients for C == 3: grid = (chunks, B); a thread accumulates the 75 tap sums + 3 plain sums over its pixels of
+// image b, the block combines them with shuffles + shared memory -> scratch[b][chunk][26][3]
+__global__ void __launch_bounds__(256)
+dw5x5_wgrad_c3_kernel(const float* __restrict__ x, const float* __restrict__ dh, float* __restrict__ scratch, int H,
+                      int W, int nchunk) {
+    __shared__ float red[8][78];
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int HW = H * W;
+    const float* xb = x + (size_t)b * HW * 3;
+    const float* db = dh + (size_t)b * HW * 3;
+    float acc[26][3];
+#pragma unroll
+    for (int t = 0; t < 26; ++t)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) acc[t][c] = 0.f;
+    for (int p = chunk * blockDim.x + threadIdx.x; p < HW; p += nchunk * blockDim.x) {
+        const int w = p % W, h = p / W;
+        float g[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            g[c] = __ldg(db + (size_t)p * 3 + c);
+            acc[25][c] += g[c];
+        }
+#pragma unroll
+        for (int ky = 0; ky < 5; ++ky) {
+            const int hh = h + ky - 2;
+            if (hh < 0 || hh >= H) continue;
+            const float* row = xb + (size_t)(p + (ky - 2) * W) * 3;
+#pragma unroll
+            for (int kx = 0; kx < 5; ++kx) {
+                const int ww = w + kx - 2;
+                if (ww < 0 || ww >= W) continue;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) acc[ky * 5 + kx][c] = fmaf(__ldg(row + (kx - 2) * 3 + c), g[c], acc[ky * 5 + kx][c]);
+            }
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int t = 0; t < 26; ++t)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float s = warp_sum(acc[t][c]);
+            if (lane == 0) red[warp][t * 3 + c] = s;
+        }
+    __syncthreads();
+    if (threadIdx.x < 78) {
+        float s = 0.f;
+#pragma unroll
+        for (int y = 0; y < 8; ++y) s += red[y][threadIdx.x];
+        scratch[((size_t)b * nchunk + chunk) * 78 + threadIdx.x] = s;   // [26][3]: t * 3 + c
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // TMA-staged versions (C % 4 == 0).  These kernels are bound by instruction issue long before HBM (25 FMAs per
 // output plus whatever surrounds them), so the layout of the work is chosen to minimise instructions per output:
 //   * tile = 16 x 16 output pixels x 32 channels; its (16+4) x (16+4) halo box is ONE bulk-tensor copy whose
@@ -203,10 +300,10 @@ SINDDM_DEVINL void load_window_column(float (&win)[6][5], const float* base, int
     for (int k = 0; k < 6; ++k) win[k][col % 5] = base[(k * kTileCols + col) * 32];
 }
 
-template <bool ADD, bool ROUND, bool FULL>
+template <bool ADD, bool ROUND, bool FULL, bool CSUM>
 SINDDM_DEVINL void dw5x5_tile(const float* tile, int ry, int lane, const float (&wr)[5][5], float bv, float cv,
                               const float* __restrict__ addp, float* __restrict__ outp, size_t off, int C,
-                              size_t rowstride, int wvalid, bool ok_a, bool ok_b) {
+                              size_t rowstride, int wvalid, bool ok_a, bool ok_b, float& csum) {
     // residual operand of the whole tile: 32 independent loads in flight before the first FMA needs one
     float ad_a[kTW], ad_b[kTW];
     if (ADD) {
@@ -244,16 +341,26 @@ SINDDM_DEVINL void dw5x5_tile(const float* tile, int ry, int lane, const float (
             vb = round_tf32(vb);
         }
         const size_t o = off + (size_t)wo * C;
-        if (FULL || (ok_a && wo < wvalid)) outp[o] = va;
-        if (FULL || (ok_b && wo < wvalid)) outp[o + rowstride] = vb;
+        if (FULL || (ok_a && wo < wvalid)) {
+            outp[o] = va;
+            if (CSUM) csum += va;
+        }
+        if (FULL || (ok_b && wo < wvalid)) {
+            outp[o + rowstride] = vb;
+            if (CSUM) csum += vb;
+        }
     }
 }
 
-template <bool ADD, bool ROUND>
+// CSUM: the CTA also writes the per-channel sum of everything it stored to csum_part[part][C] (part = (seg, th, b));
+// the data-gradient launch of block l produces the upstream gradient of block l-1, whose bias gradient is exactly
+// that column sum -- one extra add per output instead of another full pass over the tensor.
+template <bool ADD, bool ROUND, bool CSUM>
 __global__ void __launch_bounds__(32 * kRowThreads, 2)
 dw5x5_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ wgt,
                  const float* __restrict__ bias, const float* __restrict__ cond, const float* __restrict__ add,
-                 float* __restrict__ out, int H, int W, int C, int tiles_w, int ncg, int tpc, int flip) {
+                 float* __restrict__ out, int H, int W, int C, int tiles_w, int ncg, int tpc, int flip,
+                 float* __restrict__ csum_part) {
     extern __shared__ __align__(128) uint8_t dsm[];
     float* tiles = reinterpret_cast<float*>(dsm);   // two halo boxes
     uint64_t* bar = reinterpret_cast<uint64_t*>(dsm + 2 * kTileFloats * sizeof(float));
@@ -286,6 +393,7 @@ dw5x5_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const float* __restr
     const bool rows_full = th * kTH + kTH <= H && cg * 32 + 32 <= C;   // CTA-uniform
     const size_t rowstride = (size_t)W * C;
     const size_t rowoff = ((size_t)b * H + (h < H ? h : 0)) * rowstride + cc;
+    float csum = 0.f;
 
     for (int i = 0; i < ntile; ++i) {
         const int buf = i & 1;
@@ -301,12 +409,45 @@ dw5x5_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const float* __restr
         if (rows_full && w0 + kTW <= W) {
             // (the residual operand loads are issued before the wait: they overlap the box's arrival)
             mbar_wait(&bar[buf], (uint32_t)(i >> 1) & 1u);
-            dw5x5_tile<ADD, ROUND, true>(tile, ry, lane, wr, bv, cv, add, out, off, C, rowstride, kTW, true, true);
+            dw5x5_tile<ADD, ROUND, true, CSUM>(tile, ry, lane, wr, bv, cv, add, out, off, C, rowstride, kTW, true, true,
+                                                   csum);
         } else {
             mbar_wait(&bar[buf], (uint32_t)(i >> 1) & 1u);
-            dw5x5_tile<ADD, ROUND, false>(tile, ry, lane, wr, bv, cv, add, out, off, C, rowstride, W - w0, ok_a, ok_b);
+            dw5x5_tile<ADD, ROUND, false, CSUM>(tile, ry, lane, wr, bv, cv, add, out, off, C, rowstride, W - w0, ok_a,
+                                                    ok_b, csum);
         }
         __syncthreads();   // everyone is done with `buf` before it is refilled
+    }
+    if (CSUM) {
+        float* red = tiles;   // [8][32]; the boxes are dead after the loop's last __syncthreads
+        red[ry * 32 + lane] = csum;
+        __syncthreads();
+        if (ry == 0 && cok) {
+            float t = 0.f;
+#pragma unroll
+            for (int y = 0; y < kRowThreads; ++y) t += red[y * 32 + lane];
+            const size_t part = ((size_t)seg * gridDim.y + th) * gridDim.z + b;
+            csum_part[part * C + c] = t;
+        }
+    }
+}
+
+// out[c] = sum_k part[k][C]: block = 32 channels x 8 partial-sum lanes
+__global__ void __launch_bounds__(256) csum_final_kernel(const float* __restrict__ part, int nparts, int C,
+                                                         float* __restrict__ out, float* __restrict__ out2) {
+    __shared__ float red[8][32];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    float t = 0.f;
+    if (c < C)
+        for (int k = threadIdx.y; k < nparts; k += 8) t += part[(size_t)k * C + c];
+    red[threadIdx.y][threadIdx.x] = t;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        float v = 0.f;
+#pragma unroll
+        for (int y = 0; y < 8; ++y) v += red[y][threadIdx.x];
+        out[c] = v;
+        if (out2) out2[c] = v;
     }
 }
 
@@ -412,37 +553,82 @@ static int tiles_per_cta(int tiles_w, long long ctas_per_segment, int max_tpc) {
     return tpc;
 }
 
-template <bool ADD, bool ROUND>
+template <bool ADD, bool ROUND, bool CSUM>
 static int dw5x5_tma_launch(const CUtensorMap& tm, const float* w, const float* bias, const float* cond,
-                            const float* add, float* out, int B, int H, int W, int C, int flip, cudaStream_t stream) {
+                            const float* add, float* out, int B, int H, int W, int C, int flip, cudaStream_t stream,
+                            float* csum_out, float* csum_out2, float* csum_scratch) {
     const size_t smem = 2 * kTileFloats * sizeof(float) + 16;
     static int attr_set = 0;
     if (!attr_set) {
-        SINDDM_CUDA_OK(cudaFuncSetAttribute(dw5x5_tma_kernel<ADD, ROUND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)smem));
+        SINDDM_CUDA_OK(cudaFuncSetAttribute(dw5x5_tma_kernel<ADD, ROUND, CSUM>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = 1;
     }
     const int tiles_w = ceil_div(W, kTW), tiles_h = ceil_div(H, kTH), ncg = ceil_div(C, 32);
     const int tpc = tiles_per_cta(tiles_w, (long long)ncg * tiles_h * B, kMaxTilesPerCta);
     dim3 grid(ncg * ceil_div(tiles_w, tpc), tiles_h, B);
     dim3 block(32, kRowThreads);
-    dw5x5_tma_kernel<ADD, ROUND><<<grid, block, smem, stream>>>(tm, w, bias, cond, add, out, H, W, C, tiles_w, ncg,
-                                                                 tpc, flip);
+    dw5x5_tma_kernel<ADD, ROUND, CSUM><<<grid, block, smem, stream>>>(tm, w, bias, cond, add, out, H, W, C, tiles_w,
+                                                                       ncg, tpc, flip, csum_scratch);
     SINDDM_CUDA_OK(cudaGetLastError());
+    if (CSUM) {
+        const int nparts = (int)(grid.x / ncg) * tiles_h * B;
+        csum_final_kernel<<<ncg, dim3(32, 8), 0, stream>>>(csum_scratch, nparts, C, csum_out, csum_out2);
+        SINDDM_CUDA_OK(cudaGetLastError());
+    }
     return SINDDM_OK;
 }
 
+size_t dw5x5_csum_scratch_floats(int B, int H, int W, int C) {
+    const size_t a = (size_t)ceil_div(W, kTW) * ceil_div(H, kTH) * B * C;
+    const size_t b = colsum_scratch_floats(C);
+    return a > b ? a : b;
+}
+
 int dw5x5_launch(const float* in, const float* w, const float* bias, const float* cond, const float* add, float* out,
-                 int B, int H, int W, int C, int flip, int round_tf32, cudaStream_t stream) {
+                 int B, int H, int W, int C, int flip, int round_tf32, cudaStream_t stream, float* csum_out,
+                 float* csum_out2, float* csum_scratch) {
     SINDDM_REQUIRE(B <= 65535, "dw5x5: batch too large");
+    SINDDM_REQUIRE(!csum_out || csum_scratch, "dw5x5: column sums need a scratch buffer");
     if (C % 4 == 0 && device_info().initialized) {
         CUtensorMap tm;
         SINDDM_TRY(make_tmap_nhwc(&tm, in, B, H, W, C, 32, kTileCols, kTileRows, CU_TENSOR_MAP_SWIZZLE_NONE));
+#define SINDDM_DW_ARGS tm, w, bias, cond, add, out, B, H, W, C, flip, stream, csum_out, csum_out2, csum_scratch
+        if (add && csum_out)
+            return round_tf32 ? dw5x5_tma_launch<true, true, true>(SINDDM_DW_ARGS)
+                              : dw5x5_tma_launch<true, false, true>(SINDDM_DW_ARGS);
         if (add)
-            return round_tf32 ? dw5x5_tma_launch<true, true>(tm, w, bias, cond, add, out, B, H, W, C, flip, stream)
-                              : dw5x5_tma_launch<true, false>(tm, w, bias, cond, add, out, B, H, W, C, flip, stream);
-        return round_tf32 ? dw5x5_tma_launch<false, true>(tm, w, bias, cond, add, out, B, H, W, C, flip, stream)
-                          : dw5x5_tma_launch<false, false>(tm, w, bias, cond, add, out, B, H, W, C, flip, stream);
+            return round_tf32 ? dw5x5_tma_launch<true, true, false>(SINDDM_DW_ARGS)
+                              : dw5x5_tma_launch<true, false, false>(SINDDM_DW_ARGS);
+        if (!csum_out)
+            return round_tf32 ? dw5x5_tma_launch<false, true, false>(SINDDM_DW_ARGS)
+                              : dw5x5_tma_launch<false, false, false>(SINDDM_DW_ARGS);
+        // (column sums without a residual operand: not needed by the network; separate pass below)
+        const int rc = round_tf32 ? dw5x5_tma_launch<false, true, false>(SINDDM_DW_ARGS)
+                                  : dw5x5_tma_launch<false, false, false>(SINDDM_DW_ARGS);
+        SINDDM_TRY(rc);
+#undef SINDDM_DW_ARGS
+        SINDDM_TRY(colsum_launch(out, (long long)B * H * W, C, csum_out, csum_scratch, stream));
+        if (csum_out2)
+            SINDDM_CUDA_OK(cudaMemcpyAsync(csum_out2, csum_out, sizeof(float) * C, cudaMemcpyDeviceToDevice, stream));
+        return SINDDM_OK;
+    }
+    if (csum_out) {
+        SINDDM_TRY(dw5x5_launch(in, w, bias, cond, add, out, B, H, W, C, flip, round_tf32, stream, nullptr, nullptr,
+                                nullptr));
+        SINDDM_TRY(colsum_launch(out, (long long)B * H * W, C, csum_out, csum_scratch, stream));
+        if (csum_out2)
+            SINDDM_CUDA_OK(cudaMemcpyAsync(csum_out2, csum_out, sizeof(float) * C, cudaMemcpyDeviceToDevice, stream));
+        return SINDDM_OK;
+    }
+    if (C == 3) {
+        const long long P = (long long)B * H * W;
+        const long long cap = 8ll * (device_info().initialized ? device_info().num_sms : 148);
+        const long long want = (P + 255) / 256;
+        dw5x5_c3_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, stream>>>(in, w, bias, cond, add, out, B, H, W,
+                                                                                 flip, round_tf32);
+        SINDDM_CUDA_OK(cudaGetLastError());
+        return SINDDM_OK;
     }
     const int nseg = ceil_div(W, kSeg);
     dim3 grid(nseg * ceil_div(C, 32), ceil_div(H, kRowsPerBlock), B);
@@ -482,6 +668,10 @@ int dw5x5_wgrad_launch(const float* x, const float* dh, float* dw, float* db, fl
         dim3 grid(ncg * nseg, tiles_h, B);
         dim3 block(32, kRowThreads);
         dw5x5_wgrad_tma_kernel<<<grid, block, smem, stream>>>(tm, dh, scratch, H, W, C, tiles_w, ncg, tpc, nseg);
+    } else if (C == 3) {
+        nchunk = ceil_div(H, kRowsPerChunk);
+        if (nchunk > 16) nchunk = 16;
+        dw5x5_wgrad_c3_kernel<<<dim3(nchunk, B), 256, 0, stream>>>(x, dh, scratch, H, W, nchunk);
     } else {
         nchunk = ceil_div(H, kRowsPerChunk);
         dim3 grid(ceil_div(C, 32), nchunk, B);

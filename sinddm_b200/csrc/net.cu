@@ -58,6 +58,16 @@ inline int d1_rows(int math, int Ci, int Co) {
     return (Ci < 16 && use_tc_conv(math, Co, 0, false, 16)) ? 16 : Ci;
 }
 
+// l1.net[0] as a 1x1 GEMM over im2col rows (27 patch values padded to one 32-channel chunk)
+inline bool use_im2col(int math, int Ci, int Co) {
+    ConvProblem p;
+    memset(&p, 0, sizeof(p));
+    p.Cin = 32;
+    p.N = Co;
+    p.ntaps = 1;
+    return math == MATH_TF32 && Ci == 3 && tc_conv_supported(p) && tc_wgrad_supported(32, Co);
+}
+
 bool use_tc_wgrad(int math, int Cx, int Cy) { return math == MATH_TF32 && tc_wgrad_supported(Cx, Cy); }
 
 int wgrad_nsplit(int math, int B, int H, int W, int Cx, int Cy, int ntaps) {
@@ -101,6 +111,8 @@ size_t carve(Plan* pl, uint8_t* base) {
         b.w2_d = tr ? cv.take(packed_weight_floats(9, b.Co, b.Co)) : nullptr;
         b.wr_d = (tr && b.has_res) ? cv.take(packed_weight_floats(1, b.Ci, b.Co)) : nullptr;
         b.bias2c = b.has_res ? cv.take((size_t)b.Co) : nullptr;
+        b.im2col = use_im2col(pl->math, b.Ci, b.Co);
+        b.x27 = b.im2col ? cv.take(P * 32) : nullptr;
         if (tr) {
             b.h0 = cv.take(P * b.Ci);
             b.z1 = cv.take(P * b.Co);
@@ -118,7 +130,8 @@ size_t carve(Plan* pl, uint8_t* base) {
         coff += (size_t)B * b.Ci;
         if (tr) {
             const size_t n2 = (size_t)wgrad_nsplit(pl->math, B, pl->H, pl->W, b.Co, b.Co, 9) * 9 * b.Co * b.Co;
-            const size_t n0 = (size_t)wgrad_nsplit(pl->math, B, pl->H, pl->W, b.Ci, b.Co, 9) * 9 * b.Ci * b.Co;
+            const size_t n0 = b.im2col ? (size_t)wgrad_nsplit(pl->math, B, pl->H, pl->W, 32, b.Co, 1) * 32 * b.Co
+                                       : (size_t)wgrad_nsplit(pl->math, B, pl->H, pl->W, b.Ci, b.Co, 9) * 9 * b.Ci * b.Co;
             const size_t nr = (size_t)wgrad_nsplit(pl->math, B, pl->H, pl->W, b.Ci, b.Co, 1) * b.Ci * b.Co;
             if (n2 > partial_max) partial_max = n2;
             if (n0 > partial_max) partial_max = n0;
@@ -138,7 +151,7 @@ size_t carve(Plan* pl, uint8_t* base) {
         if (nf > partial_max) partial_max = nf;
         pl->partial = cv.take(partial_max);
         pl->dw_scratch = cv.take(dw5x5_wgrad_scratch_floats(B, pl->H, dim));
-        pl->colsum_scratch = cv.take(colsum_scratch_floats(dim));
+        pl->colsum_scratch = cv.take(dw5x5_csum_scratch_floats(B, pl->H, pl->W, dim));
         pl->colsum_out = cv.take(dim);
         size_t doff = 0;
         for (int l = 0; l < kNumBlocks; ++l) {
@@ -157,13 +170,13 @@ int run_conv(bool tc, TcConvOp& op, const ConvProblem& p, cudaStream_t s) {
     return simt_conv_launch(p, s);
 }
 
-int run_wgrad(bool tc, const TcWgradOp& op, const WgradProblem& p, float* dst, cudaStream_t s) {
+int run_wgrad(bool tc, const TcWgradOp& op, const WgradProblem& p, float* dst, cudaStream_t s, int layout = 0) {
     if (tc) {
         SINDDM_TRY(tc_wgrad_launch(op, s));
     } else {
         SINDDM_TRY(simt_wgrad_launch(p, s));
     }
-    return wgrad_reduce_launch(p.partial, p.nsplit, p.ntaps, p.Cx, p.Cy, dst, 0, s);
+    return wgrad_reduce_launch(p.partial, p.nsplit, p.ntaps, p.Cx, p.Cy, dst, layout, s);
 }
 
 }  // namespace
@@ -238,7 +251,8 @@ int plan_build(Plan* pl, int B, int H, int W, int dim, int channels, int math, i
         memset(&c1, 0, sizeof(c1));
         c1.B = B; c1.H = H; c1.W = W;
         c1.in = b.h0; c1.Cin = b.Ci; c1.w = b.w0_f; c1.ntaps = 9; c1.N = b.Co;
-        b.tc_c1 = use_tc_conv(math, b.Ci, 0, false, b.Co);
+        if (b.im2col) { c1.in = b.x27; c1.Cin = 32; c1.ntaps = 1; }
+        b.tc_c1 = b.im2col || use_tc_conv(math, b.Ci, 0, false, b.Co);
         b.tc_c2 = use_tc_conv(math, b.Co, b.Ci, res_slices, b.Co);
         c1.ep.gelu = 1; c1.ep.out = b.a1; c1.ep.out_pre = tr ? b.z1 : nullptr; c1.ep.round_tf32 = rnd && b.tc_c2;
         c1.ep.fast_math = rnd;
@@ -292,9 +306,10 @@ int plan_build(Plan* pl, int B, int H, int W, int dim, int channels, int math, i
             WgradProblem& w0 = b.pw0;
             memset(&w0, 0, sizeof(w0));
             w0.B = B; w0.H = H; w0.W = W; w0.x = b.h0; w0.Cx = b.Ci; w0.dy = pl->dz1; w0.Cy = b.Co; w0.ntaps = 9;
+            if (b.im2col) { w0.x = b.x27; w0.Cx = 32; w0.ntaps = 1; }
             w0.partial = pl->partial;
-            w0.nsplit = wgrad_nsplit(math, B, H, W, b.Ci, b.Co, 9);
-            b.tc_w0 = use_tc_wgrad(math, b.Ci, b.Co);
+            w0.nsplit = wgrad_nsplit(math, B, H, W, w0.Cx, b.Co, w0.ntaps);
+            b.tc_w0 = use_tc_wgrad(math, w0.Cx, b.Co);
 
             WgradProblem& wr = b.pwr;
             memset(&wr, 0, sizeof(wr));
@@ -352,7 +367,12 @@ int net_pack_weights(Plan* pl, const float* const* params, cudaStream_t s) {
     for (int l = 0; l < kNumBlocks; ++l) {
         BlockBufs& b = pl->blk[l];
         // tensor-core layers read the blocked pre-swizzled layout, CUDA-core layers the plain [tap][N][K] one
-        if (pl->training && b.tc_d1 != b.tc_c1) {
+        if (b.im2col) {
+            SINDDM_TRY(pack_im2col_weights_launch(params[b.pbase + 6], b.Co, b.w0_f, rnd, pl->blocked_weights, s));
+            if (pl->training)
+                SINDDM_TRY(pack_conv_weights_launch(params[b.pbase + 6], b.Co, b.Ci, 9, nullptr, b.w0_d, rnd && b.tc_d1, s,
+                                                    b.tc_d1 && pl->blocked_weights, b.pd1.N));
+        } else if (pl->training && b.tc_d1 != b.tc_c1) {
             // l1: the forward conv (Cin = 3) runs on CUDA cores, its data gradient on the tensor cores
             SINDDM_TRY(pack_conv_weights_launch(params[b.pbase + 6], b.Co, b.Ci, 9, b.w0_f, nullptr, rnd && b.tc_c1, s,
                                                 b.tc_c1 && pl->blocked_weights));
@@ -411,6 +431,7 @@ int net_forward(Plan* pl, const float* const* params, const float* x_nchw, const
         // h0 = ds_conv(x) + bias + cond      (models.py:70-77)
         SINDDM_TRY(dw5x5_launch(b.in, params[b.pbase + 4], params[b.pbase + 5], b.cond, nullptr, b.h0, B, H, W, b.Ci,
                                 0, rnd && b.tc_c1, s));
+        if (b.im2col) SINDDM_TRY(im2col3x3_c3_launch(b.h0, b.x27, B, H, W, 0, s));   // h0 is already tf32-rounded
         // a1 = GELU(net[0](h0))              (models.py:63-64)
         b.pc1.ep.bias = params[b.pbase + 7];
         SINDDM_TRY(run_conv(b.tc_c1, b.c1, b.pc1, s));
@@ -446,18 +467,21 @@ int net_backward(Plan* pl, const float* const* params, const float* dout_nchw, f
         float* d_o = ((kNumBlocks - 1 - l) % 2 == 0) ? pl->d_a : pl->d_b;
         float* d_prev = (d_o == pl->d_a) ? pl->d_b : pl->d_a;
 
-        // bias gradients of net[2] (and res_conv, identical sum)
-        SINDDM_TRY(colsum_launch(d_o, P, b.Co, grads[b.pbase + 9], pl->colsum_scratch, s));
-        if (b.has_res)
-            SINDDM_CUDA_OK(cudaMemcpyAsync(grads[b.pbase + 11], grads[b.pbase + 9], sizeof(float) * b.Co,
-                                           cudaMemcpyDeviceToDevice, s));
+        // bias gradients of net[2] (and res_conv, identical sum): for l < 3 they were accumulated by the depthwise
+        // data-gradient launch that produced d_o (end of the previous iteration)
+        if (l == kNumBlocks - 1) {
+            SINDDM_TRY(colsum_launch(d_o, P, b.Co, grads[b.pbase + 9], pl->colsum_scratch, s));
+            if (b.has_res)
+                SINDDM_CUDA_OK(cudaMemcpyAsync(grads[b.pbase + 11], grads[b.pbase + 9], sizeof(float) * b.Co,
+                                               cudaMemcpyDeviceToDevice, s));
+        }
         // weight gradients of net[2] and res_conv
         SINDDM_TRY(run_wgrad(b.tc_w2, b.wg2, b.pw2, grads[b.pbase + 8], s));
         if (b.has_res) SINDDM_TRY(run_wgrad(b.tc_wr, b.wgr, b.pwr, grads[b.pbase + 10], s));
         // dz1 = conv3x3^T(d_o) * gelu'(z1)
         SINDDM_TRY(run_conv(b.tc_d2, b.d2, b.pd2, s));
         SINDDM_TRY(colsum_launch(pl->dz1, P, b.Co, grads[b.pbase + 7], pl->colsum_scratch, s));
-        SINDDM_TRY(run_wgrad(b.tc_w0, b.wg0, b.pw0, grads[b.pbase + 6], s));
+        SINDDM_TRY(run_wgrad(b.tc_w0, b.wg0, b.pw0, grads[b.pbase + 6], s, b.im2col ? 2 : 0));
         // dh0 = conv3x3^T(dz1)
         SINDDM_TRY(run_conv(b.tc_d1, b.d1, b.pd1, s));
         // depthwise weight / bias / conditioning gradients
@@ -470,8 +494,10 @@ int net_backward(Plan* pl, const float* const* params, const float* dout_nchw, f
                 SINDDM_TRY(run_conv(b.tc_dr, b.dr, b.pdr, s));
                 addp = pl->dxres;
             }
+            const BlockBufs& pb = pl->blk[l - 1];   // d_prev is its upstream gradient
             SINDDM_TRY(dw5x5_launch(pl->dh0, params[b.pbase + 4], nullptr, nullptr, addp, d_prev, B, H, W, b.Ci, 1,
-                                    rnd, s));
+                                    rnd, s, grads[pb.pbase + 9], pb.has_res ? grads[pb.pbase + 11] : nullptr,
+                                    pl->colsum_scratch));
         }
     }
 

@@ -55,6 +55,9 @@ struct BlockBufs {
     // packed weights
     float *w0_f, *w0_d, *w2_f, *w2_d, *wr_f, *wr_d;
     float* bias2c;        // net[2].bias + res_conv.bias
+    // l1 in TF32 mode: net[0] (3 -> Co, 3x3) runs as a 1x1 tensor-core GEMM over the im2col rows x27 [P,32]
+    bool im2col;
+    float* x27;
     // activations ([P, C] NHWC)
     float *h0, *z1, *a1, *o;
     const float* in;      // block input (previous block's o, or x_nhwc)

@@ -96,7 +96,7 @@ int tc_wgrad_launch(const TcWgradOp& op, cudaStream_t stream);
 int simt_wgrad_nsplit(int B, int H, int W, int Cx, int Cy, int ntaps);
 int simt_wgrad_launch(const WgradProblem& p, cudaStream_t stream);
 
-// dst (OIHW: [Cy][Cx][ntaps]) = sum_split partial;  transpose_out = 0 keeps [ntaps][Cx][Cy].
+// dst (OIHW: [Cy][Cx][ntaps]) = sum_split partial;  keep_layout = 1 keeps [ntaps][Cx][Cy], 2 = im2col rows (below).
 int wgrad_reduce_launch(const float* partial, int nsplit, int ntaps, int Cx, int Cy, float* dst, int keep_layout,
                         cudaStream_t stream);
 
@@ -108,6 +108,11 @@ int wgrad_reduce_launch(const float* partial, int nsplit, int ntaps, int Cx, int
 // dgrad_rows > Cin pads the data-gradient operand to that many rows (the extra rows are never written: clear them once).
 int pack_conv_weights_launch(const float* w, int Cout, int Cin, int ntaps, float* dst_fwd, float* dst_dgrad, int round,
                              cudaStream_t stream, int blocked = 0, int dgrad_rows = 0);
+// 3-channel 3x3 conv as a 1x1 GEMM over im2col rows: out[p][tap*3 + c] = x[p (+) tap][c] ([P,32], columns 27..31
+// zero); weights [Co][3][3][3] -> [1][Co][32]; wgrad_reduce_launch(..., keep_layout = 2) maps the [32][Co]
+// gradient of that GEMM back to OIHW.
+int im2col3x3_c3_launch(const float* x, float* out, int B, int H, int W, int round, cudaStream_t stream);
+int pack_im2col_weights_launch(const float* w, int Co, float* dst, int round, int blocked, cudaStream_t stream);
 // floats needed by a packed weight buffer in either layout ([ntaps][N][K] or blocked with K padded to 32)
 inline size_t packed_weight_floats(int ntaps, int N, int K) { return (size_t)ntaps * N * ((K + 31) / 32 * 32); }
 
@@ -115,9 +120,13 @@ inline size_t packed_weight_floats(int ntaps, int N, int K) { return (size_t)nta
 // Depthwise 5x5 (pad 2):  out[p][c] = add[p][c] + bias[c] + cond[b][c] + sum_tap w[c][tap(') ] * in[p (+) tap][c]
 //   flip = 1 correlates with the flipped kernel (data gradient).
 // ------------------------------------------------------------------------------------------------
+// csum_out != null: also csum_out[c] (and csum_out2[c]) = sum_p out[p][c], accumulated by the same kernel pass;
+// csum_scratch then needs dw5x5_csum_scratch_floats(B,H,W,C) floats.
+size_t dw5x5_csum_scratch_floats(int B, int H, int W, int C);
 int dw5x5_launch(const float* in, const float* w /*[C][25]*/, const float* bias, const float* cond /*[B][C]*/,
                  const float* add, float* out, int B, int H, int W, int C, int flip, int round_tf32,
-                 cudaStream_t stream);
+                 cudaStream_t stream, float* csum_out = nullptr, float* csum_out2 = nullptr,
+                 float* csum_scratch = nullptr);
 
 // dW[c][tap] = sum_p x[p(+)tap][c] dh[p][c];  db[c] = sum_p dh[p][c];  dcond[b][c] = sum_hw dh[b,hw][c].
 // scratch needs dw5x5_wgrad_scratch_floats(B,H,C) floats.

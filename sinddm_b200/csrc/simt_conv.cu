@@ -197,7 +197,12 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int nspli
         for (int j = 0; j < 8; ++j) s += v[j];
     }
     for (; k < nsplit; ++k) s += __ldcs(partial + (size_t)k * total + i);
-    if (keep_layout) {
+    if (keep_layout == 2) {
+        // im2col rows of a 3-channel 3x3 conv: ci row index = tap*3 + c (rows 27..31 are padding) -> OIHW [Cy][3][3][3]
+        const int co = i % Cy;
+        const int k = i / Cy;
+        if (k < 27) dst[((size_t)co * 3 + k % 3) * 9 + k / 3] = s;
+    } else if (keep_layout) {
         dst[i] = s;
     } else {
         const int co = i % Cy;
@@ -230,6 +235,45 @@ __global__ void pack_conv_weights_kernel(const float* __restrict__ w, int Cout, 
     if (round) v = round_tf32(v);
     if (dst_fwd) dst_fwd[packed_index(tap, co, ci, Cout, Cin, blocked)] = v;
     if (dst_dgrad) dst_dgrad[packed_index(ntaps - 1 - tap, ci, co, dgrad_rows, Cout, blocked)] = v;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// im2col for the one 3x3 convolution whose input has 3 channels (l1.net[0], reference SinDDM/models.py:62): its K is
+// only 27, so instead of a CUDA-core kernel the 27 patch values of every pixel are laid out as ONE 32-channel
+// (128-byte) row and the layer runs as a 1x1 tensor-core GEMM with the usual fused epilogue; the weight gradient
+// reads the same rows.  out[p][tap*3 + c] = x[p (+) tap][c], columns 27..31 = 0; 8 threads (float4 each) per pixel.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+im2col3x3_c3_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int H, int W, int round) {
+    const long long total = (long long)B * H * W * 8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int q = (int)(i & 7);
+        const long long p = i >> 3;
+        const int w = (int)(p % W), h = (int)((p / W) % H);
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = q * 4 + j;
+            const int tap = k / 3, c = k - tap * 3;
+            const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+            float t = 0.f;
+            if (k < 27 && hh >= 0 && hh < H && ww >= 0 && ww < W)
+                t = __ldg(x + (p + (long long)(tap / 3 - 1) * W + (tap % 3 - 1)) * 3 + c);
+            v[j] = round ? round_tf32(t) : t;
+        }
+        reinterpret_cast<float4*>(out)[i] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+// w [Co][3][3][3] (OIHW) -> the 1x1 GEMM operand [1][Co][32] with k = tap*3 + c, in either packed layout
+__global__ void pack_im2col_weights_kernel(const float* __restrict__ w, int Co, float* __restrict__ dst, int round,
+                                           int blocked) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Co * 27) return;
+    const int tap = i % 9, c = (i / 9) % 3, co = i / 27;
+    float v = w[i];
+    if (round) v = round_tf32(v);
+    dst[packed_index(0, co, tap * 3 + c, Co, 32, blocked)] = v;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -755,6 +799,21 @@ int wgrad_reduce_launch(const float* partial, int nsplit, int ntaps, int Cx, int
                         cudaStream_t stream) {
     const int total = ntaps * Cx * Cy;
     wgrad_reduce_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(partial, nsplit, ntaps, Cx, Cy, dst, keep_layout);
+    SINDDM_CUDA_OK(cudaGetLastError());
+    return SINDDM_OK;
+}
+
+int im2col3x3_c3_launch(const float* x, float* out, int B, int H, int W, int round, cudaStream_t stream) {
+    const long long total = (long long)B * H * W * 8;
+    const long long cap = 16ll * (device_info().initialized ? device_info().num_sms : 148);
+    const long long want = (total + 255) / 256;
+    im2col3x3_c3_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, stream>>>(x, out, B, H, W, round);
+    SINDDM_CUDA_OK(cudaGetLastError());
+    return SINDDM_OK;
+}
+
+int pack_im2col_weights_launch(const float* w, int Co, float* dst, int round, int blocked, cudaStream_t stream) {
+    pack_im2col_weights_kernel<<<ceil_div(Co * 27, 256), 256, 0, stream>>>(w, Co, dst, round, blocked);
     SINDDM_CUDA_OK(cudaGetLastError());
     return SINDDM_OK;
 }

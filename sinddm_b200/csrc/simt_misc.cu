@@ -32,12 +32,22 @@ __global__ void colsum_partial_kernel(const float* __restrict__ a, long long P, 
     }
 }
 
-__global__ void colsum_final_kernel(const float* __restrict__ scratch, int nblk, int C, float* __restrict__ out) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+// block = 32 channels x 8 lanes over the partial sums (fixed order: deterministic)
+__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ scratch, int nblk, int C,
+                                                           float* __restrict__ out) {
+    __shared__ float red[8][32];
+    const int c = blockIdx.x * 32 + threadIdx.x;
     float s = 0.f;
-    for (int k = 0; k < nblk; ++k) s += scratch[(size_t)k * C + c];
-    out[c] = s;
+    if (c < C)
+        for (int k = threadIdx.y; k < nblk; k += 8) s += scratch[(size_t)k * C + c];
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        float v = 0.f;
+#pragma unroll
+        for (int y = 0; y < 8; ++y) v += red[y][threadIdx.x];
+        out[c] = v;
+    }
 }
 
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int C, int HW) {
@@ -83,7 +93,7 @@ int colsum_launch(const float* a, long long P, int C, float* out, float* scratch
     dim3 block(C, lanes);
     colsum_partial_kernel<<<nblk, block, (size_t)lanes * C * sizeof(float), stream>>>(a, P, C, scratch);
     SINDDM_CUDA_OK(cudaGetLastError());
-    colsum_final_kernel<<<ceil_div(C, 64), 64, 0, stream>>>(scratch, nblk, C, out);
+    colsum_final_kernel<<<ceil_div(C, 32), dim3(32, 8), 0, stream>>>(scratch, nblk, C, out);
     SINDDM_CUDA_OK(cudaGetLastError());
     return SINDDM_OK;
 }

@@ -16,6 +16,8 @@ exist so external code can poke them, enabling them raises.
 """
 from __future__ import annotations
 
+import os
+import warnings
 from functools import partial
 from pathlib import Path
 
@@ -65,6 +67,23 @@ class _L1LossFn(torch.autograd.Function):
         return None, ctx.dpred * gout
 
 
+class _StepGraph:
+    """One reverse-diffusion step (denoiser evaluation + noise draw + ddpm_step + `t -= 1`) captured as a CUDA graph
+    over static tensors: replaying it n times runs n consecutive timesteps with one host call each instead of
+    ~35 kernel launches and a dozen tensor allocations (the coarse scales are launch-bound otherwise)."""
+
+    def __init__(self):
+        self.graph = None
+        self.x = None          # state, updated in place by every replay
+        self.t = None          # [B] int64, decremented by every replay
+        self.prev = None       # upsampled previous-scale sample (reblurring), or None
+        self.launches = 0      # library kernels per replay
+
+
+# library kernels executed through graph replays (they bypass the C launch counter, which counts at capture time)
+graph_replayed_launches = 0
+
+
 class MultiScaleGaussianDiffusion(nn.Module):
     def __init__(self, denoise_fn, *, save_interm=False, results_folder='/Results', n_scales, scale_factor,
                  image_sizes, scale_mul=(1, 1), channels=3, timesteps=100, train_full_t=False, scale_losses=None,
@@ -83,6 +102,8 @@ class MultiScaleGaussianDiffusion(nn.Module):
         self.img_prev_upsample = None
         self.omega = omega
         self.loss_type = loss_type
+        # sampling loops replay a captured CUDA graph per timestep (SINDDM_SAMPLE_GRAPH=0 keeps the eager loop)
+        self.use_step_graph = os.environ.get('SINDDM_SAMPLE_GRAPH', '1') != '0'
 
         # guidance hooks of the reference (models.py:193-220): present, inert, refusing to be switched on
         self.clip_guided_sampling = False
@@ -265,17 +286,87 @@ class MultiScaleGaussianDiffusion(nn.Module):
                              gammas_row=self._gamma_row(s) if reblur else None,
                              reblur_mode=reblur, clip_denoised=clip_denoised, omega=float(self.omega))
 
+    # -- CUDA-graph replay of consecutive timesteps -------------------------------------------------
+    def _step_graph_for(self, x, s, reblur):
+        """Graph of one p_sample step for this (scale, shape); lives with the denoiser's inference plan so it
+        dies with the workspace its kernels point into.  Returns None when capture is not possible."""
+        net = self.denoise_fn
+        lib = _capi.load()
+        B, ch, H, W = x.shape
+        plan = net._runtime.plan(lib, x.device, B, H, W, net.dim, ch, net.math, False)
+        graphs = plan.__dict__.setdefault('step_graphs', {})
+        key = (int(s), bool(reblur), float(self.omega), self.dp_rank, self.dp_world,
+               tuple(p.data_ptr() for p in net.parameters()), self.gammas.data_ptr(), self.betas.data_ptr())
+        sg = graphs.get(key)
+        if sg is not None:
+            return sg
+        sg = _StepGraph()
+        sg.x = torch.empty_like(x)
+        sg.t = torch.zeros((B,), device=x.device, dtype=torch.long)
+        sg.prev = torch.empty_like(x) if reblur else None
+        saved_prev = self.img_prev_upsample
+        try:
+            if reblur:
+                self.img_prev_upsample = sg.prev
+            graph = torch.cuda.CUDAGraph()
+            l0 = lib.sinddm_launch_count()
+            with torch.cuda.graph(graph):
+                out = self.p_sample(sg.x, sg.t, s)
+                sg.x.copy_(out)
+                sg.t.sub_(1)
+            sg.launches = int(lib.sinddm_launch_count() - l0)
+            sg.graph = graph
+        except Exception as e:  # capture refused (e.g. an unsupported driver): keep the eager loop
+            warnings.warn(f'sinddm_b200: CUDA-graph capture of the sampling step failed ({e}); using eager steps')
+            self.use_step_graph = False
+            sg = None
+        finally:
+            self.img_prev_upsample = saved_prev
+        if sg is not None:
+            while len(graphs) >= 4:
+                graphs.pop(next(iter(graphs)))
+            graphs[key] = sg
+        return sg
+
+    def _run_steps(self, img, s, t_hi, t_lo, total):
+        """img <- p_sample(img, i, s) for i = t_hi-1 ... t_lo (the loop of models.py:480-485 / :540-545)."""
+        global graph_replayed_launches
+        device = img.device
+        b = img.shape[0]
+        steps = list(reversed(range(t_lo, t_hi)))
+        reblur = bool(self.reblurring) and int(s) > 0
+        use_graph = (self.use_step_graph and img.is_cuda and len(steps) >= 4 and not self.save_interm
+                     and not self.clip_guided_sampling and not self.roi_guided_sampling)
+        bar = tqdm(steps, desc='sampling loop time step', total=total, disable=None)
+        if not use_graph:
+            for i in bar:
+                img = self.p_sample(img, torch.full((b,), i, device=device, dtype=torch.long), s)
+            return img
+        # first step eagerly: builds the plan and (re)packs the weights the graph's kernels read
+        it = iter(bar)
+        i0 = next(it)
+        img = self.p_sample(img, torch.full((b,), i0, device=device, dtype=torch.long), s)
+        sg = self._step_graph_for(img, s, reblur)
+        if sg is None:
+            for i in it:
+                img = self.p_sample(img, torch.full((b,), i, device=device, dtype=torch.long), s)
+            return img
+        sg.x.copy_(img)
+        sg.t.fill_(i0 - 1)
+        if reblur:
+            sg.prev.copy_(self.img_prev_upsample)
+        for _ in it:
+            sg.graph.replay()
+            graph_replayed_launches += sg.launches
+        return sg.x.clone()
+
     @torch.no_grad()
     def p_sample_loop(self, shape, s):
         """models.py:462-487"""
         device = self.betas.device
-        b = shape[0]
         img = self._randn(shape, device)
         t_min = self.num_timesteps_ideal[s + 1] if (self.sample_limited_t and s < (self.n_scales - 1)) else 0
-        for i in tqdm(reversed(range(t_min, self.num_timesteps)), desc='sampling loop time step',
-                      total=self.num_timesteps, disable=None):
-            img = self.p_sample(img, torch.full((b,), i, device=device, dtype=torch.long), s)
-        return img
+        return self._run_steps(img, s, self.num_timesteps, t_min, self.num_timesteps)
 
     @torch.no_grad()
     def sample(self, batch_size=16, scale_0_size=None, s=0):
@@ -293,9 +384,7 @@ class MultiScaleGaussianDiffusion(nn.Module):
         img = self.q_sample(x_start=img, t=torch.Tensor.expand(torch.tensor(total_t, device=device), batch_size),
                             noise=None)
         t_min = self.num_timesteps_ideal[s + 1] if (self.sample_limited_t and s < (self.n_scales - 1)) else 0
-        for i in tqdm(reversed(range(t_min, total_t)), desc='sampling loop time step', total=total_t, disable=None):
-            img = self.p_sample(img, torch.full((b,), i, device=device, dtype=torch.long), s)
-        return img
+        return self._run_steps(img, s, total_t, t_min, total_t)
 
     @torch.no_grad()
     def sample_via_scale(self, batch_size, img, s, scale_mul=(1, 1), custom_sample=False, custom_img_size_idx=0,

@@ -129,6 +129,7 @@ def test_seeded_chain_vs_reference_golden(golden, math):
     import sinddm_b200.diffusion as D
     g = golden("g5_chains.npz")
     net, dif = build(math, timesteps=12)
+    dif.use_step_graph = False      # the replayed noise comes from a CPU generator: not capturable
     assert dif.num_timesteps_ideal == list(g["T12_ideal"])
     h, w = GOLDEN_SIZES[0][1], GOLDEN_SIZES[0][0]
     gen = torch.Generator().manual_seed(5)
@@ -147,6 +148,41 @@ def test_seeded_chain_vs_reference_golden(golden, math):
     finally:
         D.noise_like = orig_nl
         dif._randn = orig_randn
+
+
+@pytest.mark.parametrize("math", ["fp32", "tf32"])
+def test_graph_replayed_sampling_equals_eager_sampling(math):
+    """The sampling loops replay one captured CUDA graph per timestep; with the same CUDA generator seed the
+    replayed chain (denoiser, noise draws, ddpm_step) must reproduce the eager chain bit for bit, at scale 0 and at
+    a reblurring scale, also when the graph is reused with a new upsampled image and after a weight update."""
+    import sinddm_b200.diffusion as D
+    net, dif = build(math, timesteps=12)
+    prev = rs_tensor(77, (2, 3, GOLDEN_SIZES[0][1], GOLDEN_SIZES[0][0]), 0.5).clamp(-1, 1).to(DEV)
+
+    def run(use_graph, seed, img):
+        dif.use_step_graph = use_graph
+        torch.manual_seed(seed)
+        a = dif.sample(batch_size=2)
+        b = dif.sample_via_scale(2, img, s=1, scale_mul=(1, 1), custom_sample=True, custom_img_size_idx=1, custom_t=7)
+        return a.clone(), b.clone()
+
+    e0, e1 = run(False, 3, prev)
+    before = D.graph_replayed_launches
+    g0, g1 = run(True, 3, prev)
+    assert D.graph_replayed_launches > before, "the graph path did not run"
+    assert torch.equal(e0, g0) and torch.equal(e1, g1)
+    # cached graphs, new seed and a different previous-scale image
+    e0, e1 = run(False, 4, -prev)
+    g0, g1 = run(True, 4, -prev)
+    assert torch.equal(e0, g0) and torch.equal(e1, g1)
+    # weights updated in place: the eager first step repacks them, the replays must see the new values
+    with torch.no_grad():
+        for p in net.parameters():
+            p.mul_(0.9)
+    e0, e1 = run(False, 5, prev)
+    g0, g1 = run(True, 5, prev)
+    assert torch.equal(e0, g0) and torch.equal(e1, g1)
+    assert torch.isfinite(g1).all()
 
 
 @pytest.mark.parametrize("math", ["fp32", "tf32"])
