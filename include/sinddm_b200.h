@@ -190,6 +190,35 @@ typedef struct sinddm_ddpm_step_desc {
 } sinddm_ddpm_step_desc;
 int sinddm_ddpm_step(const sinddm_ddpm_step_desc* desc, void* stream);
 
+/* ---- optimizer step: gradient all-reduce + Adam + EMA in one kernel ------------------------------ */
+
+/* One optimizer step of MultiscaleTrainer.train (SinDDM/trainer.py:208-213: opt.step(), opt.zero_grad(), step_ema()
+ * -> models.py:18-31) for the flat fp32 parameter vector, preceded -- when world > 1 -- by the data-parallel
+ * gradient mean the reference does not have.  grads[r] is rank r's gradient bucket of this step and flags[r] rank
+ * r's array of `world` uint32 flags (zero-initialised once), both inside a symmetric allocation that is
+ * peer-mapped into this process (NVLink P2P); the kernel synchronises the ranks through the flags
+ * (flags[dst][src] = epoch), sums the buckets in rank order, divides by world and applies Adam
+ * (torch.optim.Adam semantics, no weight decay / amsgrad) and the EMA update in the same pass.  A bucket may be
+ * rewritten only after the NEXT step's call has been enqueued (double buffer by step parity).  world == 1:
+ * grads[0] is a plain device buffer and flags are ignored. */
+#define SINDDM_FUSED_MAX_WORLD 8
+typedef struct sinddm_fused_step_desc {
+    int world, rank;
+    long long n;                 /* elements, multiple of 4 */
+    const float* grads[SINDDM_FUSED_MAX_WORLD];
+    uint32_t* flags[SINDDM_FUSED_MAX_WORLD];
+    uint32_t epoch;              /* strictly increasing per call, starts at 1 */
+    float* param;
+    float* exp_avg;
+    float* exp_avg_sq;
+    float* ema;                  /* may be NULL when ema_mode == 0 */
+    float lr, beta1, beta2, eps;
+    long long step;              /* 1-based Adam step count t (bias corrections 1 - beta^t) */
+    int ema_mode;                /* 0: none, 1: ema = param, 2: ema = ema * ema_beta + (1 - ema_beta) * param */
+    float ema_beta;
+} sinddm_fused_step_desc;
+int sinddm_fused_step(const sinddm_fused_step_desc* desc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

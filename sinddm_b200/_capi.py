@@ -52,6 +52,21 @@ class DdpmStepDesc(C.Structure):
     ]
 
 
+FUSED_MAX_WORLD = 8
+
+
+class FusedStepDesc(C.Structure):
+    """struct sinddm_fused_step_desc"""
+    _fields_ = [
+        ("world", _i), ("rank", _i), ("n", _ll),
+        ("grads", _vp * FUSED_MAX_WORLD), ("flags", _vp * FUSED_MAX_WORLD),
+        ("epoch", C.c_uint32),
+        ("param", _vp), ("exp_avg", _vp), ("exp_avg_sq", _vp), ("ema", _vp),
+        ("lr", _f), ("beta1", _f), ("beta2", _f), ("eps", _f),
+        ("step", _ll), ("ema_mode", _i), ("ema_beta", _f),
+    ]
+
+
 # name -> (restype, argtypes); must list every function include/sinddm_b200.h declares (tests check it)
 SIGNATURES = {
     "sinddm_init": (_i, [_i]),
@@ -81,6 +96,7 @@ SIGNATURES = {
     "sinddm_l1_loss_workspace_bytes": (_sz, []),
     "sinddm_l1_loss": (_i, [_vp, _vp, _ll, _vp, _vp, _vp, _sz, _vp]),
     "sinddm_ddpm_step": (_i, [C.POINTER(DdpmStepDesc), _vp]),
+    "sinddm_fused_step": (_i, [C.POINTER(FusedStepDesc), _vp]),
 }
 
 

@@ -28,6 +28,7 @@ SOURCES = [
     "dw_kernels.cu",
     "cond.cu",
     "diffusion_ops.cu",
+    "fused_optim.cu",
     "net.cu",
     "capi.cu",
 ]

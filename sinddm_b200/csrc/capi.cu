@@ -1,9 +1,13 @@
 // extern "C" surface of libsinddm_b200.so -- thin argument checking over the internal launchers.
 #include "../../include/sinddm_b200.h"
 
+#include <math.h>
+#include <string.h>
+
 #include <new>
 
 #include "diffusion_ops.h"
+#include "fused_optim.h"
 #include "net.h"
 
 using namespace sinddm;
@@ -13,6 +17,7 @@ struct sinddm_plan {
 };
 
 static_assert(SINDDM_NUM_PARAMS == kNumParams, "parameter count out of sync with net.h");
+static_assert(SINDDM_FUSED_MAX_WORLD == kFusedMaxWorld, "fused step world limit out of sync");
 
 static inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
 
@@ -225,6 +230,30 @@ int sinddm_ddpm_step(const sinddm_ddpm_step_desc* d, void* stream) {
     a.sqrt_ac = d->sqrt_alphas_cumprod; a.sqrt_1mac = d->sqrt_one_minus_alphas_cumprod;
     a.gammas = d->gammas;
     return ddpm_step_launch(a, as_stream(stream));
+}
+
+int sinddm_fused_step(const sinddm_fused_step_desc* d, void* stream) {
+    SINDDM_REQUIRE(d != nullptr, "fused_step: NULL descriptor");
+    SINDDM_REQUIRE(d->world >= 1 && d->world <= SINDDM_FUSED_MAX_WORLD, "fused_step: world=%d unsupported", d->world);
+    SINDDM_REQUIRE(d->step >= 1, "fused_step: step must be >= 1");
+    SINDDM_REQUIRE(d->beta1 >= 0.f && d->beta1 < 1.f && d->beta2 >= 0.f && d->beta2 < 1.f, "fused_step: bad betas");
+    FusedStepDesc a;
+    memset(&a, 0, sizeof(a));
+    a.world = d->world; a.rank = d->rank; a.n = d->n;
+    for (int r = 0; r < d->world; ++r) {
+        a.grads[r] = d->grads[r];
+        a.flags[r] = d->flags[r];
+    }
+    a.epoch = d->epoch;
+    a.param = d->param; a.exp_avg = d->exp_avg; a.exp_avg_sq = d->exp_avg_sq; a.ema = d->ema;
+    a.beta1 = d->beta1; a.beta2 = d->beta2; a.eps = d->eps;
+    // bias corrections in double like torch.optim.Adam's python scalars
+    const double bc1 = 1.0 - pow((double)d->beta1, (double)d->step);
+    const double bc2 = 1.0 - pow((double)d->beta2, (double)d->step);
+    a.step_size = (float)((double)d->lr / bc1);
+    a.bias2_sqrt = (float)sqrt(bc2);
+    a.ema_mode = d->ema_mode; a.ema_beta = d->ema_beta;
+    return fused_step_launch(a, as_stream(stream));
 }
 
 }  // extern "C"

@@ -23,8 +23,9 @@
 //   * operands land in 128B-swizzled K-major tiles that the UMMA descriptors consume directly.
 //   accumulators   fp32 in TMEM: three slots of N columns; tile pair p uses slots (2p, 2p+1) mod 3, so the
 //                  main loop of pair p+1 only waits for the epilogue of the FIRST half of pair p.
-//   roles          (warpgroup aligned) warp 0: TMA producer | warp 1: TMEM alloc + MMA issue (whole warps in uniform control flow,
-//                  the issuing lane is elected inside the asm: this removed a ~250-cycle/MMA issue cost)
+//   roles          (warpgroup aligned) warp 0: TMA producer | warp 1: TMEM alloc | warps 1 and 2: MMA issue, one per
+//                  M = 128 half of the tile (whole warps in uniform control flow, the issuing lane is elected inside
+//                  the asm: this removed a ~250-cycle/MMA issue cost; two issuers because one cannot feed N = 80)
 //                  warps 4-11: epilogue (TMEM -> registers -> bias/residual/GELU/... -> global), two warps per
 //                  TMEM lane quarter splitting the columns, global operands prefetched one chunk ahead
 //   grid           persistent, min(#tiles, #SMs) CTAs, static round-robin over tiles.
@@ -45,7 +46,7 @@ constexpr int kKC = 32;                      // channels per K chunk (32 fp32 = 
 constexpr int kRowBytes = kTileW * kKC * 4;  // one image row of the box: 16 px x 128 B = 2 KiB
 constexpr int kABytes = kBoxH * kRowBytes;   // 36 KiB
 constexpr int kMaxN = 160;
-constexpr int kThreads = 384;       // warp 0 TMA, warp 1 MMA, (warps 2-3 idle), warps 4-11 epilogue
+constexpr int kThreads = 384;       // warp 0 TMA, warps 1-2 MMA (one per half tile), warp 3 idle, warps 4-11 epilogue
 constexpr int kEpiWarp0 = 4;        // roles are warpgroup aligned so that setmaxnreg can move registers between them
 constexpr int kEpiThreads = 256;
 constexpr int kTmemCols = 512;
@@ -71,6 +72,7 @@ struct KernelArgs {
     const float* w_blk;        // non-null: weights in the blocked pre-swizzled layout [tap][chunk][N][32] ...
     const float* wres_blk;     // ... (and the residual 1x1 weights [chunk][N][32]): boxes come by 1-D bulk copy
     uint32_t idesc;
+    int issuers2;              // single-CTA kernel: warps 1 and 2 each issue the MMAs of one half tile (SINDDM_TC_ISSUERS=1: warp 1 issues both)
     int dbg;                   // diagnostics (SINDDM_TC_DEBUG): 1 = no operand loads, 2 = no epilogue traffic, 4 = no MMAs, 8 = stage but do not store
     ConvEpilogue ep;
 };
@@ -121,13 +123,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             tma_prefetch_desc(&tm_ares);
             if (!a.w_blk) tma_prefetch_desc(&tm_bres);
         }
+        // empty barriers: one commit per MMA-issuing warp (two in the single-CTA kernel, see below)
         for (int i = 0; i < kStagesA; ++i) {
             mbar_init(&fulla_bar[i], TWO ? 2 : 1);   // one arrival per producing CTA
-            mbar_init(&emptya_bar[i], 1);
+            mbar_init(&emptya_bar[i], (!TWO && a.issuers2) ? 2 : 1);
         }
         for (int i = 0; i < a.nstages_b; ++i) {
             mbar_init(&fullb_bar[i], TWO ? 2 : 1);
-            mbar_init(&emptyb_bar[i], 1);
+            mbar_init(&emptyb_bar[i], (!TWO && a.issuers2) ? 2 : 1);
         }
         for (int i = 0; i < kSlots; ++i) {
             mbar_init(&tfull_bar[i], 1);
@@ -240,7 +243,59 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                 }
             }
         }
-      } else if (warp == 1 && crank == 0) {
+      } else if (!TWO && a.issuers2 && (warp == 1 || warp == 2)) {
+        // ------------------------------------------------------------ MMA issuers (single-CTA kernel)
+        // Issuing a tcgen05.mma costs the issuing warp ~50-70 cycles (descriptor moves into uniform registers,
+        // election, predicates), which is as long as an N = 80 MMA executes: one issuing warp cannot keep the
+        // tensor pipe busy on the narrow layers and barely does on the wide ones.  The two M = 128 halves of a
+        // tile are independent accumulators, so warp 1 issues every MMA of the first half and warp 2 every MMA
+        // of the second half: both wait on the same full barriers, both commit to the empty barriers (count 2),
+        // each commits its own accumulator slot -- the first half no longer waits for the second one either.
+        const int half = warp - 1;
+        int sa_i = 0, sb_i = 0;
+        uint32_t pha = 0, phb = 0;
+        uint32_t slot_uses[kSlots] = {0, 0, 0};
+        int titer = 0;
+        const uint32_t desc_hi = (uint32_t)(umma_smem_desc(0, 0, 1024, UMMA_LAYOUT_SW128) >> 32);
+        for (int st = pair_id; st < nsuper; st += npairs, ++titer) {
+            const int s0 = (2 * titer) % kSlots, s1 = (2 * titer + 1) % kSlots;
+            const int slot = half ? s1 : s0;
+            // the slot must have been drained by the epilogue of its previous use (by either half)
+            mbar_wait(&tempty_bar[slot], (slot_uses[slot] & 1u) ^ 1u);
+            ++slot_uses[s0];
+            ++slot_uses[s1];
+            tc_fence_after_sync();
+            const uint32_t dacc = tmem_base + (uint32_t)(slot * a.slot_stride);
+            for (int it = 0; it < nst; ++it) {
+                const bool main = it < nst_main;
+                const int cvalid = main ? min(kKC, a.Cin - (it / nkx) * kKC) : min(kKC, a.Cres - (it - nst_main) * kKC);
+                const uint32_t nmma = (uint32_t)(cvalid >> 3);  // K = 8 tf32 per instruction, <= 4 per chunk
+                const int kys = main ? nky : 1;
+                mbar_wait(&fulla_bar[sa_i], pha);
+                const uint32_t sa = smem_u32(smem + (size_t)sa_i * kABytes);
+                for (int ky = 0; ky < kys; ++ky) {
+                    mbar_wait(&fullb_bar[sb_i], phb);
+                    tc_fence_after_sync();
+                    // vertical tap = row offset into the halo box; the 1x1 / residual case reads the centre rows
+                    const int row0 = ((main && nky == 3) ? ky : 1) + 8 * half;
+                    const uint32_t ad = ((sa + (uint32_t)row0 * kRowBytes) >> 4) & 0x3FFFu;
+                    const uint32_t bd = (smem_u32(smem_b + (size_t)sb_i * a.bbox_bytes) >> 4) & 0x3FFFu;
+                    if (!(a.dbg & 4)) umma_tf32_ss_x4(dacc, ad, bd, desc_hi, 2u, a.idesc, (it | ky) != 0 ? 1u : 0u, nmma);
+                    umma_commit_elect(&emptyb_bar[sb_i]);
+                    if (++sb_i == a.nstages_b) {
+                        sb_i = 0;
+                        phb ^= 1u;
+                    }
+                }
+                umma_commit_elect(&emptya_bar[sa_i]);
+                if (++sa_i == kStagesA) {
+                    sa_i = 0;
+                    pha ^= 1u;
+                }
+            }
+            umma_commit_elect(&tfull_bar[slot]);
+        }
+      } else if ((TWO || !a.issuers2) && warp == 1 && crank == 0) {
         // ------------------------------------------------------------ MMA issuer (leader CTA of a pair)
         int sa_i = 0, sb_i = 0;
         uint32_t pha = 0, phb = 0;
@@ -664,6 +719,10 @@ int tc_conv_launch(const TcConvOp& op, cudaStream_t stream) {
     a.idesc = umma_idesc_tf32(op.cs == 2 ? 256 : 128, p.N, 0, 0);
     a.w_blk = p.w_blocked ? p.w : nullptr;
     a.wres_blk = p.w_blocked ? p.w_res : nullptr;
+    {
+        const char* e = getenv("SINDDM_TC_ISSUERS");
+        a.issuers2 = e ? (atoi(e) != 1) : 1;
+    }
     {
         const char* e = getenv("SINDDM_TC_DEBUG");   // diagnostic runs only: results are wrong when set
         a.dbg = e ? atoi(e) : 0;

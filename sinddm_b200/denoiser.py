@@ -105,6 +105,8 @@ class _Runtime:
     def __init__(self):
         self.plans = OrderedDict()
         self.freqs = {}
+        self.weights_epoch = 0      # bumped when a kernel updated the parameters in place (fused optimizer step)
+        self.grad_bucket = None     # flat fp32 tensor backward writes the 52 gradients into (fused optimizer step)
 
     def __deepcopy__(self, memo):
         return _Runtime()
@@ -142,7 +144,7 @@ class _NetFunction(torch.autograd.Function):
         plan = net._runtime.plan(lib, x.device, B, H, W, net.dim, ch, net.math, want_grad)
         stream = torch.cuda.current_stream(x.device).cuda_stream
         parr = _ptr_array(params)
-        pkey = tuple((p.data_ptr(), p._version) for p in params)
+        pkey = (net._runtime.weights_epoch, tuple((p.data_ptr(), p._version) for p in params))
         if plan.packed_key != pkey:
             check(lib.sinddm_net_pack_weights(plan.handle, parr, stream), "sinddm_net_pack_weights")
             plan.packed_key = pkey
@@ -153,6 +155,10 @@ class _NetFunction(torch.autograd.Function):
         if want_grad:
             ctx.plan = plan
             ctx.generation = plan.generation
+            bucket = net._runtime.grad_bucket
+            if bucket is not None and bucket.numel() != sum(p.numel() for p in params):
+                raise _capi.SinddmError("gradient bucket size does not match the parameters")
+            ctx.grad_bucket = bucket
             ctx.save_for_backward(*params)
         return out
 
@@ -168,11 +174,16 @@ class _NetFunction(torch.autograd.Function):
         dout = dout.contiguous()
         stream = torch.cuda.current_stream(dout.device).cuda_stream
         sizes = [p.numel() for p in params]
-        flat = torch.empty(sum(sizes), dtype=torch.float32, device=dout.device)
+        bucket = ctx.grad_bucket
+        flat = bucket if bucket is not None else torch.empty(sum(sizes), dtype=torch.float32, device=dout.device)
         views = list(flat.split(sizes))
         grads = [v.view_as(p) for v, p in zip(views, params)]
         check(lib.sinddm_net_backward(plan.handle, _ptr_array(params), dout.data_ptr(), _ptr_array(grads), stream),
               "sinddm_net_backward")
+        if bucket is not None:
+            # fused optimizer step: the gradients stay in the bucket (consumed by sinddm_fused_step), autograd
+            # does not accumulate them into .grad
+            return (None,) * (5 + len(params))
         return (None, None, None, None, None, *grads)
 
 
@@ -220,6 +231,16 @@ class SinDDMNet(nn.Module):
             f = SinusoidalPosEmb(32).frequencies(device).float().contiguous()
             self._runtime.freqs[device] = f
         return f
+
+    def mark_weights_updated(self):
+        """Call after the parameters were modified outside autograd's version tracking (raw kernels): the packed
+        convolution weights of every plan are rebuilt before the next forward."""
+        self._runtime.weights_epoch += 1
+
+    def set_grad_bucket(self, bucket):
+        """Flat fp32 CUDA tensor (sum of parameter sizes) that backward fills instead of returning gradients to
+        autograd; None restores the normal `.grad` path."""
+        self._runtime.grad_bucket = bucket
 
     def _check_supported(self):
         # The reference itself only works with multiscale=True (`if exists(self.multiscale)` is always true,

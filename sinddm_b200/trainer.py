@@ -126,6 +126,7 @@ class MultiscaleTrainer(object):
         self.bucket = spdist.GradientBucket(ms_diffusion_model.parameters())
 
         self.step = 0
+        self._fused = None          # set by _prepare_training()
         self.running_loss = []
         self.running_scale = []
         self.avg_t = []
@@ -188,12 +189,17 @@ class MultiscaleTrainer(object):
                 s = torch.multinomial(input=self._s_weights, num_samples=1)
         s = int(s)                                        # the reference syncs here too (list index by tensor)
         loss = None
+        fused = self._fused
+        if fused is not None:
+            # backward writes the 52 gradients straight into this step's (peer-mapped) bucket
+            self.model.denoise_fn.set_grad_bucket(fused.bucket())
         for _ in range(self.gradient_accumulate_every):
             batch = self.data_list[s]
             loss = self.model(batch, s)
             self._loss_acc += loss.detach().double()
             loss_backwards(self.fp16, loss / self.gradient_accumulate_every, self.opt)
-        self.bucket.all_reduce_mean()
+        if fused is None:
+            self.bucket.all_reduce_mean()
         if self.step % self.avg_window == 0:
             acc = self._loss_acc.clone()
             if self.world > 1:
@@ -205,15 +211,41 @@ class MultiscaleTrainer(object):
                 print(f'step:{self.step} loss:{avg}')
             self.running_loss.append(avg)
             self._loss_acc.zero_()
-        self.opt.step()
-        self.opt.zero_grad()
-        if self.step % self.update_ema_every == 0:
-            self.step_ema()
+        if fused is not None:
+            # one kernel: gradient mean over the ranks (NVLink peer loads), Adam, EMA (trainer.py:208-213)
+            ema_mode = 0
+            if self.step % self.update_ema_every == 0:
+                ema_mode = 1 if self.step < self.step_start_ema else 2
+            fused.step(self.opt.param_groups[0]['lr'], ema_mode, self.ema.beta)
+        else:
+            self.opt.step()
+            self.opt.zero_grad()
+            if self.step % self.update_ema_every == 0:
+                self.step_ema()
         self.scheduler.step()
         self.step += 1
         return loss
 
+    def _make_fused_step(self):
+        """The fused all-reduce + Adam + EMA step (sinddm_b200.fused_optim) when the configuration allows it:
+        CUDA, one micro-batch per optimizer step, SINDDM_FUSED_STEP != 0.  Otherwise torch.optim.Adam + NCCL."""
+        import os
+        net = getattr(self.model, 'denoise_fn', None)
+        ok = (os.environ.get('SINDDM_FUSED_STEP', '1') != '0' and self.gradient_accumulate_every == 1
+              and net is not None and hasattr(net, 'set_grad_bucket')
+              and next(net.parameters()).is_cuda)
+        if not ok:
+            return None
+        from .fused_optim import FusedStep
+        group = self.opt.param_groups[0]
+        fused = FusedStep(net, self.ema_model.denoise_fn, betas=group['betas'], eps=group['eps'])
+        self.opt._opt_called = True      # the scheduler only reads the learning rate from this optimizer now
+        return fused
+
     def _prepare_training(self):
+        if self._fused is None and not getattr(self, '_fused_decided', False):
+            self._fused = self._make_fused_step()
+            self._fused_decided = True
         self._s_weights = torch.tensor(self.model.num_timesteps_trained, device=self.device, dtype=torch.float)
         self._s_weights_host = self._s_weights.cpu()
         if not hasattr(self, '_host_gen'):
