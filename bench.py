@@ -205,11 +205,24 @@ def run_b200_arm(args):
     from sinddm_b200 import MultiScaleGaussianDiffusion, MultiscaleTrainer, SinDDMNet, _capi
     from sinddm_b200 import dist as spdist
 
-    rank, local_rank, world = spdist.init_process_group()
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py --impl b200 needs a CUDA device; there is no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = f"cuda:{local_rank}"
+    # NCCL prints its version banner on stdout when the communicator is created (NCCL_DEBUG=VERSION): send
+    # everything written to fd 1 during initialisation to stderr so that stdout carries the JSON line only
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        rank, local_rank, world = spdist.init_process_group()
+        torch.cuda.set_device(local_rank)
+        dev = f"cuda:{local_rank}"
+        if world > 1:
+            tdist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     lib = _capi.load()
     _capi.init(local_rank)
     torch.manual_seed(0)

@@ -164,6 +164,15 @@ SINDDM_DEVINL void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t*
         : "memory");
 }
 
+// Brings a box into L2 only (no shared-memory destination, no completion tracking): later TMA loads of the same
+// box hit L2 instead of paying the DRAM latency.
+SINDDM_DEVINL void tma_prefetch_l2_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+
 // Tile store shared -> global (elements outside the tensor are clipped).  Completion is tracked per issuing
 // thread in bulk async-groups: commit after the store, wait_group_read<N> before the staging buffer of all but
 // the N most recent groups is overwritten.  The smem writes being stored need fence_proxy_async_smem() first.

@@ -46,7 +46,7 @@ constexpr int kKC = 32;                      // channels per K chunk (32 fp32 = 
 constexpr int kRowBytes = kTileW * kKC * 4;  // one image row of the box: 16 px x 128 B = 2 KiB
 constexpr int kABytes = kBoxH * kRowBytes;   // 36 KiB
 constexpr int kMaxN = 160;
-constexpr int kThreads = 384;       // warp 0 TMA, warps 1-2 MMA (one per half tile), warp 3 idle, warps 4-11 epilogue
+constexpr int kThreads = 384;       // warp 0 TMA, warps 1-2 MMA (one per half tile), warp 3 optional L2 prefetcher, warps 4-11 epilogue
 constexpr int kEpiWarp0 = 4;        // roles are warpgroup aligned so that setmaxnreg can move registers between them
 constexpr int kEpiThreads = 256;
 constexpr int kTmemCols = 512;
@@ -73,6 +73,7 @@ struct KernelArgs {
     const float* wres_blk;     // ... (and the residual 1x1 weights [chunk][N][32]): boxes come by 1-D bulk copy
     uint32_t idesc;
     int issuers2;              // single-CTA kernel: warps 1 and 2 each issue the MMAs of one half tile (SINDDM_TC_ISSUERS=1: warp 1 issues both)
+    int l2pf;                  // warp 3 prefetches the streamed epilogue operand into L2 one tile ahead (SINDDM_TC_L2PF=1)
     int dbg;                   // diagnostics (SINDDM_TC_DEBUG): 1 = no operand loads, 2 = no epilogue traffic, 4 = no MMAs, 8 = stage but do not store
     ConvEpilogue ep;
 };
@@ -143,6 +144,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         if (TWO) tmem_alloc_2sm(tmem_slot, kTmemCols);
         else tmem_alloc(tmem_slot, kTmemCols);
     }
+    if (warp == 2 && lane == 0) tmem_slot[1] = 0u;   // tiles started by the MMA warps (read by the L2 prefetcher)
     if (warp >= kEpiWarp0) {
         const int t = threadIdx.x - kEpiWarp0 * 32;
         for (int i = t; i < N; i += kEpiThreads) s_bias[i] = a.ep.bias ? a.ep.bias[i] : 0.f;
@@ -265,6 +267,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             ++slot_uses[s0];
             ++slot_uses[s1];
             tc_fence_after_sync();
+            if (half == 0 && lane == 0) *reinterpret_cast<volatile uint32_t*>(&tmem_slot[1]) = (uint32_t)titer + 1u;
             const uint32_t dacc = tmem_base + (uint32_t)(slot * a.slot_stride);
             for (int it = 0; it < nst; ++it) {
                 const bool main = it < nst_main;
@@ -294,6 +297,27 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                 }
             }
             umma_commit_elect(&tfull_bar[slot]);
+        }
+      } else if (!TWO && a.issuers2 && a.l2pf && warp == 3 && (a.ep.res_add || a.ep.dgelu_z) && !(a.dbg & 2)) {
+        // ------------------------------------------------------------ L2 prefetcher of the streamed epilogue operand
+        // The epilogue warps stream the residual / saved pre-activation tile by tile with ONE box in flight per
+        // warp (shared memory is spent on the operand rings), i.e. 16 KiB per SM against a DRAM latency of
+        // ~2500 cycles: ~1.6 TB/s chip-wide, slower than the MMAs.  This otherwise idle warp requests the boxes of
+        // a tile into L2 one tile ahead of the MMA warps (paced by their progress counter, so the ~24 MB in
+        // flight chip-wide stay far below the L2 capacity); the epilogue's loads then pay L2 latency only.
+        const CUtensorMap* pm = &tm_in;
+        const int nch = N / kEpiChunk;
+        int t_local = 0;
+        for (int st = pair_id; st < nsuper; st += npairs, ++t_local) {
+            while ((int)*reinterpret_cast<volatile uint32_t*>(&tmem_slot[1]) < t_local) __nanosleep(256);
+            const int tile = st;
+            const int tw = tile % a.tiles_w;
+            const int th = (tile / a.tiles_w) % a.tiles_h;
+            const int b = tile / (a.tiles_w * a.tiles_h);
+            for (int idx = lane; idx < nch * (kTileH / 2); idx += 32) {
+                const int hq = th * kTileH + (idx % (kTileH / 2)) * 2;
+                if (hq < a.H) tma_prefetch_l2_4d(pm, (idx / (kTileH / 2)) * kEpiChunk, tw * kTileW, hq, b);
+            }
         }
       } else if ((TWO || !a.issuers2) && warp == 1 && crank == 0) {
         // ------------------------------------------------------------ MMA issuer (leader CTA of a pair)
@@ -719,6 +743,10 @@ int tc_conv_launch(const TcConvOp& op, cudaStream_t stream) {
     a.idesc = umma_idesc_tf32(op.cs == 2 ? 256 : 128, p.N, 0, 0);
     a.w_blk = p.w_blocked ? p.w : nullptr;
     a.wres_blk = p.w_blocked ? p.w_res : nullptr;
+    {
+        const char* e = getenv("SINDDM_TC_L2PF");    // measured neutral (profiles/): off unless asked for
+        a.l2pf = e ? (atoi(e) != 0) : 0;
+    }
     {
         const char* e = getenv("SINDDM_TC_ISSUERS");
         a.issuers2 = e ? (atoi(e) != 1) : 1;

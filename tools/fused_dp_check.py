@@ -3,8 +3,8 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/fused_dp_check.py
 
 Every rank fills its gradient bucket with rank-dependent values; sinddm_fused_step (peer loads over NVLink +
-Adam + EMA) must give the parameters that NCCL all_reduce / world + torch.optim.Adam give, identically on every
-rank.  Prints FUSED_DP_OK and the per-step device time of both paths."""
+Adam + EMA) must give the parameters that (sum of the gathered buckets in rank order) / world + torch.optim.Adam
+give, bit-identically on every rank.  Prints FUSED_DP_OK and the per-step device time of both paths."""
 import copy
 import os
 import sys
@@ -35,9 +35,20 @@ def main():
     for it in range(6):
         bucket = fused.bucket()
         bucket.copy_(torch.randn(bucket.numel(), device=dev, generator=g) * 1e-2)
-        flat = bucket.clone()
-        dist.all_reduce(flat)
-        flat /= world
+        # reference gradient mean with the kernel's association order (rank 0 + rank 1 + ...): NCCL's ring / tree /
+        # in-switch orders differ in the last bits, which Adam's normalisation amplifies wherever the ranks'
+        # gradients cancel -- that comparison is reported separately below
+        gathered = [torch.empty_like(bucket) for _ in range(world)]
+        dist.all_gather(gathered, bucket.clone())
+        flat = gathered[0].clone()
+        for r in range(1, world):
+            flat += gathered[r]
+        flat *= 1.0 / world
+        nccl = bucket.clone()
+        dist.all_reduce(nccl)
+        nccl /= world
+        nccl_grad_diff = max(locals().get("nccl_grad_diff", 0.0),
+                             float((nccl - flat).abs().max() / (flat.abs().max() + 1e-30)))
         for p, v in zip(ref_net.parameters(), flat.split([q.numel() for q in ref_net.parameters()])):
             p.grad = v.view_as(p).clone()
         fused.step(1e-3, 1 if it == 0 else 2, 0.995)
@@ -77,7 +88,8 @@ def main():
     t_fused = timed(lambda: fused.step(1e-3, 2, 0.995))
     t_nccl = timed(nccl_path)
     if rank == 0:
-        print(f"FUSED_DP_OK world={world} max_rel_diff={worst:.2e} fused_step_ms={t_fused:.4f} "
+        print(f"FUSED_DP_OK world={world} max_rel_diff={worst:.2e} replicas_bit_identical=True "
+              f"nccl_vs_ordered_sum_grad_rel_diff={nccl_grad_diff:.2e} fused_step_ms={t_fused:.4f} "
               f"nccl_allreduce_plus_adam_ms={t_nccl:.4f}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
