@@ -5,10 +5,10 @@
                    --load_milestone 12
     python -m torch.distributed.run --nproc-per-node 8 main.py --mode train ...     # data parallel over 8 B200
 
-Every flag of the reference (main.py:15-58) is accepted.  Modes `train` and `sample` run on the sm_100a
-kernels; the guidance / editing modes (clip_content, clip_style_gen, clip_style_trans, clip_roi, roi,
-harmonization, style_transfer) are outside this repo's scope and exit with
-a clear message instead of importing CLIP.
+Every flag of the reference (main.py:15-58) is accepted.  Modes `train`, `sample`, `harmonization` and
+`style_transfer` run on the sm_100a kernels; the CLIP / ROI modes (clip_content, clip_style_gen,
+clip_style_trans, clip_roi, roi) are outside this repo's scope and exit with a
+clear message instead of importing CLIP.
 """
 from __future__ import annotations
 
@@ -22,15 +22,14 @@ from SinDDM.models import MultiScaleGaussianDiffusion, SinDDMNet
 from SinDDM.trainer import MultiscaleTrainer
 from sinddm_b200 import dist as spdist
 
-OUT_OF_SCOPE_MODES = ("clip_content", "clip_style_gen", "clip_style_trans", "clip_roi", "roi", "harmonization",
-                      "style_transfer")
+OUT_OF_SCOPE_MODES = ("clip_content", "clip_style_gen", "clip_style_trans", "clip_roi", "roi")
 
 
 def build_parser():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scope", default="forest", help="choose training scope.")
-    ap.add_argument("--mode", help="train | sample (the guidance / editing modes of the reference are out of scope)")
-    # flags of the out-of-scope modes: accepted so existing command lines parse, unused here
+    ap.add_argument("--mode", help="train | sample | harmonization | style_transfer (the CLIP / ROI modes of the reference are out of scope)")
+    # harmonization / style transfer inputs; the CLIP / ROI flags are accepted so existing command lines parse
     ap.add_argument("--input_image", default="seascape_composite_dragon.png")
     ap.add_argument("--start_t_harm", default=5, type=int)
     ap.add_argument("--start_t_style", default=15, type=int)
@@ -74,8 +73,8 @@ def main(argv=None):
     args = build_parser().parse_args(argv)
     if args.mode in OUT_OF_SCOPE_MODES:
         sys.exit(f"--mode {args.mode} is outside the scope of sinddm_b200 (train and sample are implemented)")
-    if args.mode not in ("train", "sample"):
-        sys.exit("--mode must be train or sample")
+    if args.mode not in ("train", "sample", "harmonization", "style_transfer"):
+        sys.exit("--mode must be train, sample, harmonization or style_transfer")
 
     rank, local_rank, world = spdist.init_process_group()
     if rank == 0:
@@ -111,6 +110,19 @@ def main(argv=None):
 
     if args.load_milestone > 0:
         trainer.load(milestone=args.load_milestone)
+    if args.mode in ("harmonization", "style_transfer"):
+        # reference main.py:294-320: start at the last scale from t = start_t_style / start_t_harm
+        import os
+        start_s = n_scales - 1
+        use_hist = args.mode == "style_transfer"
+        custom_t = [0] * (n_scales - 1) + [args.start_t_style if use_hist else args.start_t_harm]
+        trainer.ema_model.reblurring = True
+        trainer.image2image(input_folder=os.path.join(args.dataset_folder, "i2i"), input_file=args.input_image,
+                            mask=args.harm_mask, hist_ref_path=f"{args.dataset_folder}scale_{start_s}/",
+                            batch_size=args.sample_batch_size, image_name=args.image_name, start_s=start_s,
+                            custom_t=custom_t, scale_mul=(1, 1), device=device, use_hist=use_hist, save_unbatched=True,
+                            auto_scale=50000, mode=args.mode)
+        return
     if args.mode == "train":
         trainer.train()
     trainer.sample_scales(scale_mul=scale_mul, custom_sample=True, image_name=args.image_name,

@@ -2,8 +2,10 @@
 
 Only the helpers on the hot path's boundary are here: small utilities, the cosine schedule, `extract`,
 `noise_like` and the pyramid builder `create_img_scales` (called by main.py before any model exists).
-Harmonization / CLIP / ROI helpers (dilate_mask, thresholded_grad, stat_from_bbs, extract_patch) are out of
-scope.
+`dilate_mask` and `match_histograms` serve image2image (harmonization / style transfer); the
+reference takes them from scikit-image 0.19.3 (requirements.txt:26), which this image does not have, so their
+published algorithms are restated on scipy.ndimage / numpy.  CLIP / ROI helpers (thresholded_grad, stat_from_bbs,
+extract_patch) are out of scope.
 """
 from __future__ import annotations
 
@@ -118,3 +120,67 @@ def create_img_scales(foldername, filename, scale_factor=1.411, image_size=None,
             out_dir.mkdir(parents=True, exist_ok=True)
             blurry.save(str(out_dir / png_name))
     return sizes, rescale_losses, scale_factor, n_scales
+
+
+# ---------------------------------------------------------------------------------------------------
+# image2image helpers (reference SinDDM/functions.py:21-33 and skimage.exposure.match_histograms)
+# ---------------------------------------------------------------------------------------------------
+
+def _disk(radius: int) -> np.ndarray:
+    """skimage.morphology.disk: (2r+1)^2 footprint of the pixels with x^2 + y^2 <= r^2."""
+    yy, xx = np.mgrid[-radius:radius + 1, -radius:radius + 1]
+    return (xx * xx + yy * yy) <= radius * radius
+
+
+def dilate_mask(mask, mode):
+    """functions.py:21-33: binary dilation by a disk (radius 7 for harmonization, 20 for editing), Gaussian blur
+    (sigma 5, skimage defaults: mode='nearest', truncate=4), min-max normalisation.  `mask` is a [C,H,W] tensor in
+    [0,1] (transforms.ToTensor of the mask image); only channel 0 is used, any non-zero value is foreground.
+    Returns a float64 numpy array [1,1,H,W] like the reference."""
+    from scipy import ndimage as ndi
+    if mode == "harmonization":
+        element = _disk(7)
+    elif mode == "editing":
+        element = _disk(20)
+    else:
+        raise ValueError(f"dilate_mask: unknown mode {mode!r}")
+    m = np.asarray(mask.detach().cpu() if torch.is_tensor(mask) else mask)[0] != 0
+    m = ndi.binary_dilation(m, structure=element)
+    m = ndi.gaussian_filter(m.astype(np.float64), sigma=5, mode="nearest", truncate=4.0)
+    m = m[None, None, :, :]
+    return (m - m.min()) / (m.max() - m.min())
+
+
+def _match_cumulative_cdf(source: np.ndarray, template: np.ndarray) -> np.ndarray:
+    """skimage/exposure/histogram_matching.py::_match_cumulative_cdf (0.19): map every source value to the template
+    value of the same quantile (linear interpolation between template quantiles)."""
+    if source.dtype.kind == "u":
+        src_lookup = source.reshape(-1)
+        src_counts = np.bincount(src_lookup)
+        tmpl_counts = np.bincount(template.reshape(-1))
+        tmpl_values = np.nonzero(tmpl_counts)[0]
+        tmpl_counts = tmpl_counts[tmpl_values]
+    else:
+        _, src_lookup, src_counts = np.unique(source.reshape(-1), return_inverse=True, return_counts=True)
+        tmpl_values, tmpl_counts = np.unique(template.reshape(-1), return_counts=True)
+    src_quantiles = np.cumsum(src_counts) / source.size
+    tmpl_quantiles = np.cumsum(tmpl_counts) / template.size
+    interp_a_values = np.interp(src_quantiles, tmpl_quantiles, tmpl_values)
+    return interp_a_values[src_lookup].reshape(source.shape)
+
+
+def match_histograms(image: np.ndarray, reference: np.ndarray, channel_axis=None) -> np.ndarray:
+    """skimage.exposure.match_histograms (0.19.3, what trainer.py:313 calls with channel_axis=2): per channel CDF
+    matching; the result has the dtype of `image` (uint8 images come back as uint8, values truncated)."""
+    if image.ndim != reference.ndim:
+        raise ValueError("Image and reference must have the same number of channels.")
+    if channel_axis is None:
+        return _match_cumulative_cdf(image, reference).astype(image.dtype, copy=False)
+    image = np.moveaxis(image, channel_axis, -1)
+    reference = np.moveaxis(reference, channel_axis, -1)
+    if image.shape[-1] != reference.shape[-1]:
+        raise ValueError("Number of channels in the input image and reference image must match!")
+    matched = np.empty(image.shape, dtype=image.dtype)
+    for ch in range(image.shape[-1]):
+        matched[..., ch] = _match_cumulative_cdf(image[..., ch], reference[..., ch])
+    return np.moveaxis(matched, -1, channel_axis)

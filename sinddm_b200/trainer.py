@@ -5,8 +5,9 @@ Same constructor keywords, attributes (`model`, `ema_model`, `data_list`, `opt`,
 order per step (multinomial -> randint -> randn, quirk Q7).  New here: data-parallel training under torchrun
 (sinddm_b200.dist) and a loss read-back only every `avg_window` steps instead of a host sync per step.
 
-image2image / clip_sampling / clip_roi_sampling / roi_guided_sampling are out of scope (SURVEY.md section 2,
-rows 7-9) and raise NotImplementedError.
+`image2image` (harmonization / style transfer) runs on the same sampler; clip_sampling /
+clip_roi_sampling / roi_guided_sampling are out of scope and raise
+NotImplementedError.
 """
 from __future__ import annotations
 
@@ -331,8 +332,75 @@ class MultiscaleTrainer(object):
         return samples
 
     # ---------------------------------------------------------------------------------------------
-    def image2image(self, *args, **kwargs):
-        raise NotImplementedError('harmonization / style transfer is outside the sinddm_b200 hot path')
+    def image2image(self, input_folder='', input_file='', mask='', hist_ref_path='', image_name='', start_s=1,
+                    custom_t=None, batch_size=16, scale_mul=(1, 1), device=None, use_hist=False, save_unbatched=True,
+                    auto_scale=None, mode=None, save_images=True):
+        """trainer.py:287-361: harmonization / style transfer = inject the (histogram-matched) input image at scale
+        `start_s`, noise it to custom_t[s] and run the reverse chain of the remaining scales on the EMA model; for
+        harmonization the result is blended with the input through the dilated, blurred mask.  Returns the list of
+        per-scale batches (the last one is the final composite in [0, 1])."""
+        import os
+
+        import numpy as np
+
+        from .functions import dilate_mask, match_histograms
+        device = self.device if device is None else device
+        if custom_t is None:
+            custom_t = self.ema_model.num_timesteps_ideal
+        input_img = Image.open(os.path.join(input_folder, input_file)).convert("RGB")
+        image_size = input_img.size
+        if auto_scale is not None:
+            scaler = np.sqrt((image_size[0] * image_size[1]) / auto_scale)
+            if scaler > 1:
+                image_size = (int(image_size[0] / scaler), int(image_size[1] / scaler))
+                input_img = input_img.resize(image_size, Image.LANCZOS)
+        if mode == 'harmonization':
+            mask_img = Image.open(os.path.join(input_folder, mask)).convert("RGB").resize(image_size, Image.LANCZOS)
+            mask_ten = torch.from_numpy(np.asarray(mask_img, dtype=np.uint8).copy()).permute(2, 0, 1).float().div(255)
+            mask_img = torch.from_numpy(dilate_mask(mask_ten, mode=mode)).to(device=device, dtype=torch.float32)
+        else:
+            mask_img = 1
+        if use_hist:
+            image_name = image_name.rsplit(".", 1)[0] + '.png'
+            orig_sample_0 = Image.open(hist_ref_path + image_name).convert("RGB")
+            input_img = Image.fromarray(match_histograms(image=np.array(input_img), reference=np.array(orig_sample_0),
+                                                         channel_axis=2))
+        input_img_tensor = _to_model_range(input_img)
+        input_size = input_img_tensor.shape[1:]
+        input_img_batch = input_img_tensor.repeat(batch_size, 1, 1, 1).to(device)
+
+        out_dir = Path(str(self.results_folder / 'i2i_final_samples'))
+        if save_images and self.rank == 0:
+            out_dir.mkdir(parents=True, exist_ok=True)
+        t_string = '_'.join(str(e) for e in custom_t)
+        time = str(datetime.datetime.now()).replace(":", "_")
+        if start_s > 0:  # the starting scale has no mixing between blurry and clean images (in place, like the reference)
+            self.ema_model.gammas[start_s - 1].clamp_(0, 0)
+        samples, final_img = [], None
+        for i in range(self.n_scales - start_s):
+            s = i + start_s
+            ds_factor = self.scale_factor ** (self.n_scales - s - 1)
+            cur_size = (int(input_size[0] / ds_factor), int(input_size[1] / ds_factor))
+            src = input_img_batch if i == 0 else samples[i - 1]
+            samples.append(self.ema_model.sample_via_scale(batch_size, src, s=s, custom_t=custom_t[s],
+                                                           scale_mul=scale_mul, custom_image_size=cur_size))
+            final_img = (samples[i] + 1) * 0.5
+            if i == self.n_scales - start_s - 1:
+                denorm = ((input_img_batch + 1) * 0.5).clamp_(0.0, 1.0)
+                final_img = mask_img * final_img + (1 - mask_img) * denorm
+                samples[i] = final_img
+            if save_images and self.rank == 0:
+                from torchvision import utils
+                stem = input_file.rsplit(".", 1)[0]
+                utils.save_image(final_img, str(out_dir / f'{stem}_i2i_s_{start_s + i}_t_{t_string}_hist_'
+                                                          f'{"on" if use_hist else "off"}_{time}.png'), nrow=4)
+        if save_images and save_unbatched and self.rank == 0:
+            from torchvision import utils
+            out_dir = Path(str(self.results_folder / f'unbatched_i2i_s{start_s}_t_{t_string}_{time}'))
+            out_dir.mkdir(parents=True, exist_ok=True)
+            for b in range(batch_size):
+                utils.save_image(final_img[b], os.path.join(out_dir, input_file + f'_out_b{b}_i2i.png'))
+        return samples
 
     def clip_sampling(self, *args, **kwargs):
         raise NotImplementedError('CLIP-guided sampling is outside the sinddm_b200 hot path')

@@ -228,6 +228,28 @@ def test_tensor_core_path_vs_cuda_core_twin_full_size():
         tol_check(net_tc(x, t, s), net_32(x, t, s), "tf32", "forward")
 
 
+@pytest.mark.parametrize("case", [("seascape finest, 16 per GPU (configs[3])", 16, 200, 249),
+                                  ("starry_night x(2,2) finest, 8 per GPU (configs[4])", 8, 396, 504),
+                                  ("starry_night x(2,2) coarsest", 8, 98, 124)])
+def test_other_baseline_shapes_tensor_core_vs_cuda_core_twin(case):
+    """The denoiser at the shapes of BASELINE.json's seascape / starry_night configs (sizes that are not multiples
+    of the 16-pixel tiles, 400x500 images): tcgen05 path against its fp32 CUDA-core twin (first 2 images, the fp32 twin
+    is slow), and batch rows independent of the batch size."""
+    _, B, H, W = case
+    sizes = [(W, H)]
+    net_tc, _ = build("tf32", sizes=sizes, losses=[])
+    net_32, _ = build("fp32", sizes=sizes, losses=[])
+    x = rs_tensor(31, (B, 3, H, W), 0.5).clamp(-1, 1).to(DEV)
+    t = (torch.arange(B, device=DEV) * 11) % 100
+    with torch.no_grad():
+        y = net_tc(x, t, 0)
+        assert torch.isfinite(y).all()
+        y32 = net_32(x[:2].contiguous(), t[:2].contiguous(), 0)
+        tol_check(y[:2], y32, "tf32", "forward")
+        y2 = net_tc(x[:2].contiguous(), t[:2].contiguous(), 0)
+        assert torch.allclose(y[:2], y2, rtol=0, atol=1e-6 * float(y.abs().max()))
+
+
 def test_full_size_batch32_properties():
     """Size-independent properties at the headline configuration (186x248, batch 32, TF32 path):
     identical rows give identical outputs; a batch row equals the same sample run alone; the gradient of a

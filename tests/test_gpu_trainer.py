@@ -73,3 +73,43 @@ def test_trainer_bookkeeping_and_loss_decreases(tmp_path):
     # EMA: hard copy until step 20, exponential average afterwards -> differs from the live model, stays finite
     diffs = [float((a - b).abs().max()) for a, b in zip(tr.model.parameters(), tr.ema_model.parameters())]
     assert max(diffs) > 0 and all(np.isfinite(diffs))
+
+
+def test_harmonization_and_style_transfer_modes(tmp_path):
+    """image2image (trainer.py:287-361) through the CLI after a short training run: files are written, the
+    harmonized composite equals the input image away from the (dilated, blurred) mask and differs inside it."""
+    from PIL import Image
+    sys.path.insert(0, str(REPO))
+    import main as cli
+    ds = str(tmp_path / "data") + "/"
+    _image(ds)
+    res = str(tmp_path / "results")
+    torch.manual_seed(0)
+    cli.main(["--scope", "synth", "--mode", "train", "--dataset_folder", ds, "--image_name", "synth.png",
+              "--results_folder", res, "--train_num_steps", "6", "--train_batch_size", "4",
+              "--save_and_sample_every", "6", "--avg_window", "3", "--sample_batch_size", "2"])
+    i2i = Path(ds) / "i2i"
+    i2i.mkdir()
+    base = np.asarray(Image.open(Path(ds) / "synth.png").convert("RGB")).copy()
+    comp = base.copy()
+    comp[30:50, 40:70] = [255, 40, 40]                       # pasted object
+    Image.fromarray(comp).save(i2i / "composite.png")
+    mask = np.zeros(base.shape[:2], dtype=np.uint8)
+    mask[30:50, 40:70] = 255
+    Image.fromarray(np.stack([mask] * 3, -1)).save(i2i / "mask.png")
+    common = ["--scope", "synth", "--dataset_folder", ds, "--image_name", "synth.png", "--results_folder", res,
+              "--load_milestone", "1", "--sample_batch_size", "2", "--input_image", "composite.png"]
+    cli.main(common + ["--mode", "harmonization", "--harm_mask", "mask.png", "--start_t_harm", "5"])
+    cli.main(common + ["--mode", "style_transfer", "--start_t_style", "8"])
+    out = Path(res) / "synth"
+    harm = sorted(out.glob("unbatched_i2i_s*_t_*5_*/composite.png_out_b0_i2i.png"))
+    style = sorted(out.glob("unbatched_i2i_s*_t_*8_*/composite.png_out_b0_i2i.png"))
+    assert len(harm) == 1 and len(style) == 1
+    assert len(list((out / "i2i_final_samples").glob("composite_i2i_s_*_hist_off_*.png"))) == 1
+    assert len(list((out / "i2i_final_samples").glob("composite_i2i_s_*_hist_on_*.png"))) == 1
+    h = np.asarray(Image.open(harm[0]).convert("RGB")).astype(int)
+    assert h.shape == comp.shape
+    far = np.ones(mask.shape, bool)
+    far[0:80, 10:100] = False                                 # > 7 px dilation + 4 sigma of blur away from the mask
+    assert np.abs(h[far] - comp.astype(int)[far]).max() <= 1  # untouched outside the mask (8-bit rounding)
+    assert np.abs(h[35:45, 45:65] - comp.astype(int)[35:45, 45:65]).max() > 1

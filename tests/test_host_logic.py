@@ -91,7 +91,7 @@ def test_guidance_modes_refuse_loudly():
     dif.clip_guided_sampling = True
     with pytest.raises(NotImplementedError):
         dif._refuse_guidance()
-    for name in ("image2image", "clip_sampling", "clip_roi_sampling", "roi_guided_sampling"):
+    for name in ("clip_sampling", "clip_roi_sampling", "roi_guided_sampling"):
         with pytest.raises(NotImplementedError):
             getattr(MultiscaleTrainer, name)(None)
 
@@ -133,3 +133,47 @@ def test_cli_accepts_the_reference_flags():
     assert args.sched_k_milestones == [20, 40, 70, 80, 90, 110] and args.scale_mul == [1.0, 1.0]
     with pytest.raises(SystemExit):
         cli.main(["--mode", "clip_content"])
+
+
+def test_dilate_mask_matches_the_published_skimage_pipeline():
+    """functions.py:21-33 restated on scipy (skimage 0.19.3 is absent): disk dilation + sigma-5 blur + min-max."""
+    from scipy import ndimage as ndi
+    from sinddm_b200.functions import dilate_mask
+    m = torch.zeros(3, 60, 80)
+    m[:, 25:35, 30:50] = 0.7            # any non-zero value is foreground
+    out = dilate_mask(m, mode="harmonization")
+    assert out.shape == (1, 1, 60, 80) and out.dtype == np.float64
+    assert out.min() == 0.0 and out.max() == 1.0
+    assert out[0, 0, 30, 40] == 1.0 and out[0, 0, 0, 0] < 1e-6
+    # radius-7 disk: the binary support grows by exactly 7 pixels along the axes before the blur
+    yy, xx = np.mgrid[-7:8, -7:8]
+    dil = ndi.binary_dilation(m[0].numpy() != 0, structure=(xx * xx + yy * yy) <= 49)
+    assert dil[25 - 7, 40] and not dil[25 - 8, 40] and dil[30, 30 - 7] and not dil[30, 30 - 8]
+    assert not dil[25 - 6, 30 - 6]                                   # disk, not square
+    ref = ndi.gaussian_filter(dil.astype(np.float64), 5, mode="nearest", truncate=4.0)
+    assert np.allclose(out[0, 0], (ref - ref.min()) / (ref.max() - ref.min()))
+    big = dilate_mask(m, mode="editing")
+    assert (big >= out - 1e-12).all() and big.sum() > out.sum()
+    with pytest.raises(ValueError):
+        dilate_mask(m, mode="nope")
+
+
+def test_match_histograms_is_cdf_matching_per_channel():
+    """skimage.exposure.match_histograms (trainer.py:313) restated: uint8 in -> uint8 out, per channel, identity on
+    itself, monotone, and the matched image takes the reference's quantiles."""
+    from sinddm_b200.functions import match_histograms
+    rs = np.random.RandomState(0)
+    img = rs.randint(0, 120, size=(40, 50, 3)).astype(np.uint8)
+    ref = (rs.beta(2, 5, size=(30, 70, 3)) * 255).astype(np.uint8)
+    out = match_histograms(img, ref, channel_axis=2)
+    assert out.dtype == np.uint8 and out.shape == img.shape
+    assert np.array_equal(match_histograms(img, img, channel_axis=2), img)
+    for c in range(3):
+        order = np.argsort(img[..., c].ravel(), kind="stable")
+        assert (np.diff(out[..., c].ravel()[order].astype(int)) >= 0).all()          # monotone mapping
+        for q in (0.1, 0.5, 0.9):
+            assert abs(np.quantile(out[..., c], q) - np.quantile(ref[..., c], q)) <= 3
+    f = match_histograms(img.astype(np.float64), ref.astype(np.float64), channel_axis=2)
+    assert f.dtype == np.float64 and np.abs(f - out).max() < 1.0 + 1e-9               # uint8 result = truncation
+    with pytest.raises(ValueError):
+        match_histograms(img, ref[..., :2], channel_axis=2)
