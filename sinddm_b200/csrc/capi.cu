@@ -86,7 +86,7 @@ int sinddm_conv_forward(const sinddm_conv_desc* d, int math, void* stream) {
     p.ep.bias = d->bias; p.ep.res_add = d->res_add; p.ep.x3 = d->x3; p.ep.w_res3 = d->w_res3;
     p.ep.gelu = d->gelu; p.ep.out_pre = d->out_pre; p.ep.dgelu_z = d->dgelu_z;
     p.ep.w_final = d->w_final; p.ep.b_final = d->b_final; p.ep.out_final = d->out_final;
-    p.ep.round_tf32 = d->round_tf32; p.ep.out = d->out; p.ep.out3 = nullptr; p.ep.fast_math = 0;
+    p.ep.round_tf32 = d->round_tf32; p.ep.out = d->out; p.ep.out3 = nullptr; p.ep.pre_grad = 0; p.ep.fast_math = 0;
     SINDDM_REQUIRE(p.B >= 1 && p.H >= 1 && p.W >= 1 && p.Cin >= 1 && p.N >= 1, "conv_forward: bad shape");
     SINDDM_REQUIRE(!p.ep.x3 || p.ep.w_res3, "conv_forward: x3 given without w_res3");
     SINDDM_REQUIRE(!p.ep.w_final || p.ep.out_final, "conv_forward: w_final given without out_final");

@@ -279,6 +279,11 @@ int plan_build(Plan* pl, int B, int H, int W, int dim, int channels, int math, i
             d2.Cin = b.Co; d2.w = b.w2_d; d2.ntaps = 9; d2.N = b.Co;
             d2.ep.dgelu_z = b.z1; d2.ep.out = pl->dz1; d2.ep.round_tf32 = rnd;
             b.tc_d2 = use_tc_conv(math, b.Co, 0, false, b.Co);
+            // both ends on the tensor-core path: z1 carries gelu'(pre-activation) instead of the pre-activation
+            {
+                const char* e = getenv("SINDDM_PRE_GRAD");     // A/B switch; default on
+                if (b.tc_c1 && b.tc_d2 && !(e && atoi(e) == 0)) { c1.ep.pre_grad = 1; d2.ep.pre_grad = 1; }
+            }
 
             ConvProblem& d1 = b.pd1;
             memset(&d1, 0, sizeof(d1));

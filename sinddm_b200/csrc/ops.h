@@ -32,6 +32,9 @@ struct ConvEpilogue {
     float* out;             // [P,N], or null when only out_final / out3 is wanted
     float* out3;            // tensor-core path only: [P,3] NHWC copy of result columns 0..2 (a 3-channel result computed
                             // with N padded to 16 zero weight rows), or null
+    int pre_grad;           // tensor-core path: out_pre receives gelu'(pre-activation) instead of the pre-activation, and
+                            // dgelu_z already holds gelu'(z) (the forward epilogue has cdf and pdf at hand: two extra
+                            // instructions there replace ~25 + two MUFU per value in the data-gradient epilogue)
     int fast_math;          // CUDA-core kernels: use the TF32-mode GELU (gelu_fast) instead of erff (set with math = tf32)
 };
 

@@ -711,6 +711,7 @@ __global__ void __launch_bounds__(384, 2) simt_wgrad_cx3_kernel(const WgradProbl
 int simt_conv_launch(const ConvProblem& p, cudaStream_t stream) {
     SINDDM_REQUIRE(p.ntaps == 9 || p.ntaps == 1, "simt_conv: ntaps must be 9 or 1");
     SINDDM_REQUIRE(p.N >= 1 && p.Cin >= 1, "simt_conv: bad channel counts");
+    SINDDM_REQUIRE(!p.ep.pre_grad && !p.ep.out3, "simt_conv: pre_grad / out3 are tensor-core epilogue options");
     const long long P = (long long)p.B * p.H * p.W;
     if (p.Cin == 3 && p.in_res == nullptr && p.N % 4 == 0 && p.N <= 512 && !p.ep.x3 && !p.ep.w_final) {
         const int n4 = p.N / 4;

@@ -546,19 +546,42 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                             v[4 * q + 3] += cur[q].w;
                         }
                     }
-                    if (ep.out_pre && live) store_tile(&tm_pre, cc, v);
-                    if (ep.gelu) {
+                    if (ep.gelu && ep.pre_grad && ep.out_pre) {
+                        // save gelu'(z) for the backward pass instead of z: cdf and pdf are both at hand here
+                        float g[16];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = gelu_fast(v[j]);
+                        for (int j = 0; j < 16; ++j) {
+                            float cdf, pdf;
+                            phi_cdf_pdf(v[j], &cdf, &pdf);
+                            g[j] = fmaf(v[j], pdf, cdf);
+                            v[j] *= cdf;
+                        }
+                        if (live) store_tile(&tm_pre, cc, g);
+                    } else {
+                        if (ep.out_pre && live) store_tile(&tm_pre, cc, v);
+                        if (ep.gelu) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[j] = gelu_fast(v[j]);
+                        }
                     }
                     if (ep.dgelu_z) {
                         const float4* z = gsrc2 ? pre2 : cur;
+                        if (ep.pre_grad) {
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            v[4 * q + 0] *= gelu_grad_fast(z[q].x);
-                            v[4 * q + 1] *= gelu_grad_fast(z[q].y);
-                            v[4 * q + 2] *= gelu_grad_fast(z[q].z);
-                            v[4 * q + 3] *= gelu_grad_fast(z[q].w);
+                            for (int q = 0; q < 4; ++q) {
+                                v[4 * q + 0] *= z[q].x;
+                                v[4 * q + 1] *= z[q].y;
+                                v[4 * q + 2] *= z[q].z;
+                                v[4 * q + 3] *= z[q].w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                v[4 * q + 0] *= gelu_grad_fast(z[q].x);
+                                v[4 * q + 1] *= gelu_grad_fast(z[q].y);
+                                v[4 * q + 2] *= gelu_grad_fast(z[q].z);
+                                v[4 * q + 3] *= gelu_grad_fast(z[q].w);
+                            }
                         }
                     }
                     if (ep.w_final) {

@@ -102,8 +102,8 @@ def test_harmonization_and_style_transfer_modes(tmp_path):
     cli.main(common + ["--mode", "harmonization", "--harm_mask", "mask.png", "--start_t_harm", "5"])
     cli.main(common + ["--mode", "style_transfer", "--start_t_style", "8"])
     out = Path(res) / "synth"
-    harm = sorted(out.glob("unbatched_i2i_s*_t_*5_*/composite.png_out_b0_i2i.png"))
-    style = sorted(out.glob("unbatched_i2i_s*_t_*8_*/composite.png_out_b0_i2i.png"))
+    harm = sorted(out.glob("unbatched_i2i_s*_t_*_5_20*/composite.png_out_b0_i2i.png"))
+    style = sorted(out.glob("unbatched_i2i_s*_t_*_8_20*/composite.png_out_b0_i2i.png"))
     assert len(harm) == 1 and len(style) == 1
     assert len(list((out / "i2i_final_samples").glob("composite_i2i_s_*_hist_off_*.png"))) == 1
     assert len(list((out / "i2i_final_samples").glob("composite_i2i_s_*_hist_on_*.png"))) == 1
