@@ -160,6 +160,9 @@ class MultiscaleTrainer(object):
             'running_scale': self.running_scale,
         }
         torch.save(payload, str(self.results_folder / f'model-{milestone}.pt'))
+        # new: the reference's checkpoint has no optimizer state (quirk Q12), so a resumed run
+        # restarts Adam's moments; the state goes into a SEPARATE file so that model-N.pt keeps the reference's keys
+        torch.save(self._optimizer_state(), str(self.results_folder / f'optim-{milestone}.pt'))
         try:
             from matplotlib import pyplot as plt
         except Exception:
@@ -179,6 +182,61 @@ class MultiscaleTrainer(object):
         self.ema_model.load_state_dict(ckpt['ema'])
         self.scheduler.load_state_dict(ckpt['sched'])
         self.running_loss = ckpt['running_loss']
+        opt_path = self.results_folder / f'optim-{milestone}.pt'
+        if opt_path.exists():       # absent for checkpoints written by the reference: Adam restarts, like there
+            self._set_optimizer_state(torch.load(str(opt_path), map_location='cpu'))
+
+    def _optimizer_state(self):
+        """Adam state in one layout for both optimizer implementations: step count + flat moments (parameter order)."""
+        sizes = [p.numel() for p in self.model.parameters()]
+        if self._fused is not None:
+            n = sum(sizes)
+            return {'step': int(self._fused.t), 'lr': float(self.opt.param_groups[0]['lr']),
+                    'exp_avg': self._fused.exp_avg[:n].detach().cpu().clone(),
+                    'exp_avg_sq': self._fused.exp_avg_sq[:n].detach().cpu().clone()}
+        pending = getattr(self, '_pending_optim', None)
+        if pending is not None and not self.opt.state:
+            return pending
+        step, m, v = 0, [], []
+        for p, k in zip(self.model.parameters(), sizes):
+            st = self.opt.state.get(p, {})
+            step = max(step, int(st['step']) if 'step' in st else 0)
+            m.append(st['exp_avg'].detach().reshape(-1).cpu() if 'exp_avg' in st else torch.zeros(k))
+            v.append(st['exp_avg_sq'].detach().reshape(-1).cpu() if 'exp_avg_sq' in st else torch.zeros(k))
+        return {'step': step, 'lr': float(self.opt.param_groups[0]['lr']), 'exp_avg': torch.cat(m),
+                'exp_avg_sq': torch.cat(v)}
+
+    def _set_optimizer_state(self, state):
+        self._pending_optim = state
+        if getattr(self, '_fused_decided', False):
+            self._apply_optimizer_state()
+
+    def _apply_optimizer_state(self):
+        state = getattr(self, '_pending_optim', None)
+        if state is None:
+            return
+        self._pending_optim = None
+        params = list(self.model.parameters())
+        sizes = [p.numel() for p in params]
+        if state['exp_avg'].numel() != sum(sizes):
+            raise ValueError('optimizer checkpoint does not match the model parameters')
+        if 'lr' in state:
+            # the scheduler state alone does not restore the optimizer's learning rate (the reference resumes at
+            # train_lr until the next milestone); with the optimizer file the run continues where it stopped
+            for group in self.opt.param_groups:
+                group['lr'] = float(state['lr'])
+        if self._fused is not None:
+            n = sum(sizes)
+            self._fused.t = int(state['step'])
+            self._fused.exp_avg[:n].copy_(state['exp_avg'])
+            self._fused.exp_avg_sq[:n].copy_(state['exp_avg_sq'])
+            return
+        if int(state['step']) == 0:
+            return
+        for p, m, v in zip(params, state['exp_avg'].split(sizes), state['exp_avg_sq'].split(sizes)):
+            self.opt.state[p] = {'step': torch.tensor(float(state['step'])),
+                                 'exp_avg': m.view_as(p).to(p.device).clone(),
+                                 'exp_avg_sq': v.view_as(p).to(p.device).clone()}
 
     # ---------------------------------------------------------------------------------------------
     def train_step(self, s=None):
@@ -247,6 +305,7 @@ class MultiscaleTrainer(object):
         if self._fused is None and not getattr(self, '_fused_decided', False):
             self._fused = self._make_fused_step()
             self._fused_decided = True
+            self._apply_optimizer_state()      # state loaded before the optimizer implementation was chosen
         self._s_weights = torch.tensor(self.model.num_timesteps_trained, device=self.device, dtype=torch.float)
         self._s_weights_host = self._s_weights.cpu()
         if not hasattr(self, '_host_gen'):

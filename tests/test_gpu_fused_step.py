@@ -120,3 +120,41 @@ def test_two_rank_fused_step_equals_nccl_allreduce_plus_adam():
     proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
     assert "FUSED_DP_OK" in proc.stdout
+
+
+@pytest.mark.parametrize("kinds", [(True, True), (False, False), (True, False)])
+def test_optimizer_state_checkpoint_resumes_adam(tmp_path, kinds):
+    """optim-N.pt next to model-N.pt (whose keys stay the reference's).  A run resumed from the
+    pair continues exactly like the uninterrupted run -- also across the two optimizer implementations -- whereas
+    the reference's checkpoint alone restarts Adam's moments (quirk Q12)."""
+    save_fused, load_fused = kinds
+    a = _trainer(tmp_path / "a", save_fused)
+    torch.manual_seed(3)
+    for i in range(5):
+        a.train_step(s=i % 3)
+    a.save(1)
+    assert set(torch.load(a.results_folder / "model-1.pt", map_location="cpu")) == {
+        "step", "model", "ema", "sched", "running_loss", "running_scale"}
+    torch.manual_seed(4)
+    for i in range(3):
+        a.train_step(s=i % 3)
+    want = [p.detach().clone() for p in a.model.parameters()]
+
+    b = _trainer(tmp_path / "a", load_fused)          # same results folder
+    b.load(1)
+    assert b.step == 5
+    torch.manual_seed(4)
+    for i in range(3):
+        b.train_step(s=i % 3)
+    worst = max(float((x - y).abs().max() / (y.abs().max() + 1e-12)) for x, y in zip(b.model.parameters(), want))
+    assert worst <= (1e-6 if save_fused == load_fused else 2e-3), worst
+
+    # without the optimizer file the moments restart and the continuation visibly differs
+    (a.results_folder / "optim-1.pt").unlink()
+    c = _trainer(tmp_path / "a", load_fused)
+    c.load(1)
+    torch.manual_seed(4)
+    for i in range(3):
+        c.train_step(s=i % 3)
+    drift = max(float((x - y).abs().max() / (y.abs().max() + 1e-12)) for x, y in zip(c.model.parameters(), want))
+    assert drift > 10 * max(worst, 1e-6)
