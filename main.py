@@ -66,6 +66,8 @@ def build_parser():
     ap.add_argument("--loss_factor", default=1, type=float)
     # new: numerics of the dense convolutions (tf32 tensor cores | fp32 CUDA cores)
     ap.add_argument("--math", default=None, choices=["tf32", "fp32"])
+    # new: keep the pyramid in memory instead of writing scale_i/ and scale_i_recon/ next to the image
+    ap.add_argument("--in_memory_pyramid", action="store_true")
     return ap
 
 
@@ -85,13 +87,19 @@ def main(argv=None):
     results_folder = args.results_folder + "/" + args.scope
 
     # the pyramid is written next to the dataset image: only rank 0 creates it, everyone reads it
-    if rank == 0:
-        create_img_scales(args.dataset_folder, args.image_name, scale_factor=args.scale_factor, create=True,
-                          auto_scale=50000)
-    if world > 1:
-        torch.distributed.barrier()
-    sizes, rescale_losses, scale_factor, n_scales = create_img_scales(
-        args.dataset_folder, args.image_name, scale_factor=args.scale_factor, create=False, auto_scale=50000)
+    pyramid = None
+    if args.in_memory_pyramid:
+        sizes, rescale_losses, scale_factor, n_scales, pyramid = create_img_scales(
+            args.dataset_folder, args.image_name, scale_factor=args.scale_factor, create=False, auto_scale=50000,
+            return_pyramid=True)
+    else:
+        if rank == 0:
+            create_img_scales(args.dataset_folder, args.image_name, scale_factor=args.scale_factor, create=True,
+                              auto_scale=50000)
+        if world > 1:
+            torch.distributed.barrier()
+        sizes, rescale_losses, scale_factor, n_scales = create_img_scales(
+            args.dataset_folder, args.image_name, scale_factor=args.scale_factor, create=False, auto_scale=50000)
 
     model = SinDDMNet(dim=args.dim, multiscale=True, device=device, math=args.math).to(device)
     diffusion = MultiScaleGaussianDiffusion(
@@ -106,7 +114,8 @@ def main(argv=None):
         train_batch_size=args.train_batch_size, train_lr=args.train_lr, train_num_steps=args.train_num_steps,
         gradient_accumulate_every=args.grad_accumulate, ema_decay=0.995, fp16=False,
         save_and_sample_every=args.save_and_sample_every, avg_window=args.avg_window,
-        sched_milestones=[k * 1000 for k in args.sched_k_milestones], results_folder=results_folder, device=device)
+        sched_milestones=[k * 1000 for k in args.sched_k_milestones], results_folder=results_folder, device=device,
+        pyramid=pyramid)
 
     if args.load_milestone > 0:
         trainer.load(milestone=args.load_milestone)

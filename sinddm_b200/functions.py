@@ -74,8 +74,13 @@ def cosine_beta_schedule(timesteps, s=0.008):
     return np.clip(betas, a_min=0, a_max=0.999)
 
 
-def create_img_scales(foldername, filename, scale_factor=1.411, image_size=None, create=False, auto_scale=None):
+def create_img_scales(foldername, filename, scale_factor=1.411, image_size=None, create=False, auto_scale=None,
+                      return_pyramid=False):
     """Pyramid builder, functions.py:130-192.
+
+    return_pyramid=True (new) appends a fifth result: [(level_i, blurry_i or None)] as PIL
+    images -- exactly what create=True writes to scale_i/ and scale_i_recon/ (PNG is lossless), so
+    MultiscaleTrainer(pyramid=...) can train without a writable dataset folder.
 
     Returns (sizes [(W, H) per scale], rescale_losses, adjusted scale_factor, n_scales) and, with create=True,
     writes <folder>/scale_i/<name>.png and <folder>/scale_i_recon/<name>.png.  Bit-compatible with the
@@ -111,14 +116,18 @@ def create_img_scales(foldername, filename, scale_factor=1.411, image_size=None,
         pyramid.append(level)
 
     rescale_losses = []
+    recons = [None]
     for i in range(n_scales - 1):
         blurry = pyramid[i].resize(sizes[i + 1], Image.BILINEAR)
         diff = np.subtract(pyramid[i + 1], blurry)          # uint8 arithmetic, wraps (Q1)
         rescale_losses.append(np.linalg.norm(diff) / np.asarray(blurry).size)
+        recons.append(blurry)
         if create:
             out_dir = Path(foldername + "scale_" + str(i + 1) + "_recon/")
             out_dir.mkdir(parents=True, exist_ok=True)
             blurry.save(str(out_dir / png_name))
+    if return_pyramid:
+        return sizes, rescale_losses, scale_factor, n_scales, list(zip(pyramid, recons))
     return sizes, rescale_losses, scale_factor, n_scales
 
 

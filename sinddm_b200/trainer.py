@@ -73,7 +73,7 @@ class MultiscaleTrainer(object):
                  image_sizes=None, train_batch_size=32, train_lr=2e-5, train_num_steps=100000,
                  gradient_accumulate_every=2, fp16=False, step_start_ema=2000, update_ema_every=10,
                  save_and_sample_every=25000, avg_window=100, sched_milestones=None, results_folder='./results',
-                 device=None, scale_draw='device'):
+                 device=None, scale_draw='device', pyramid=None):
         super().__init__()
         self.device = device
         self.sched_milestones = [10000, 30000, 60000, 80000, 90000] if sched_milestones is None else sched_milestones
@@ -111,7 +111,19 @@ class MultiscaleTrainer(object):
             self.results_folder.mkdir(parents=True, exist_ok=True)
 
         # one (orig, blurry) batch per scale, resident on the device for the whole run (trainer.py:120-132)
-        for i in range(n_scales):
+        if pyramid is not None:
+            # in-memory pyramid from create_img_scales(..., return_pyramid=True): the same tensors the PNG round trip
+            # through scale_i/ and scale_i_recon/ gives, without touching the dataset folder
+            if len(pyramid) != n_scales:
+                raise ValueError(f'pyramid has {len(pyramid)} levels, n_scales is {n_scales}')
+            n = min(self.local_batch, 128)                  # the reference's Dataset yields at most 128 rows
+            for i, (level, blurry) in enumerate(pyramid):
+                self.input_paths.append((folder or '') + 'scale_' + str(i))
+                self.ds_list.append(None)
+                orig = _to_model_range(level).unsqueeze(0).repeat(n, 1, 1, 1)
+                other = _to_model_range(blurry).unsqueeze(0).repeat(n, 1, 1, 1) if i > 0 else orig.clone()
+                self.data_list.append((orig.to(self.device), other.to(self.device)))
+        for i in range(n_scales if pyramid is None else 0):
             self.input_paths.append(folder + 'scale_' + str(i))
             ds = Dataset(self.input_paths[i], image_sizes[i] if i < len(image_sizes) else None, blurry_img=i > 0)
             self.ds_list.append(ds)

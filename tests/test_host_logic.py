@@ -177,3 +177,30 @@ def test_match_histograms_is_cdf_matching_per_channel():
     assert f.dtype == np.float64 and np.abs(f - out).max() < 1.0 + 1e-9               # uint8 result = truncation
     with pytest.raises(ValueError):
         match_histograms(img, ref[..., :2], channel_axis=2)
+
+
+def test_in_memory_pyramid_equals_the_png_round_trip(tmp_path):
+    """MultiscaleTrainer(pyramid=...) holds bit-identical training tensors to the reference flow
+    (create_img_scales(create=True) -> scale_i/*.png -> Dataset), for an RGB and an RGBA source image."""
+    from PIL import Image
+    from sinddm_b200 import MultiScaleGaussianDiffusion, MultiscaleTrainer, SinDDMNet, create_img_scales
+    rs = np.random.RandomState(3)
+    for mode in ("RGB", "RGBA"):
+        folder = str(tmp_path / mode) + "/"
+        (tmp_path / mode).mkdir()
+        arr = rs.randint(0, 255, (120, 160, len(mode)), dtype=np.uint8)
+        Image.fromarray(arr, mode).save(folder + "img.png")
+        sizes, losses, sf, ns, pyr = create_img_scales(folder, "img.png", create=True, auto_scale=50000,
+                                                       return_pyramid=True)
+        assert len(pyr) == ns and pyr[0][1] is None and [p[0].size for p in pyr] == sizes
+        assert (sizes, losses, sf, ns) == create_img_scales(folder, "img.png", create=False, auto_scale=50000)
+        net = SinDDMNet(dim=16, multiscale=True)
+        dif = MultiScaleGaussianDiffusion(denoise_fn=net, n_scales=ns, scale_factor=sf, image_sizes=sizes,
+                                          timesteps=100, train_full_t=True, scale_losses=losses,
+                                          results_folder=str(tmp_path / "r"))
+        kw = dict(n_scales=ns, scale_factor=sf, image_sizes=sizes, train_batch_size=3,
+                  results_folder=str(tmp_path / "r"), device="cpu")
+        from_files = MultiscaleTrainer(dif, folder, **kw)
+        from_memory = MultiscaleTrainer(dif, None, pyramid=pyr, **kw)
+        for (a0, a1), (b0, b1) in zip(from_files.data_list, from_memory.data_list):
+            assert torch.equal(a0, b0) and torch.equal(a1, b1) and a0.shape[0] == 3
