@@ -73,6 +73,7 @@ struct KernelArgs {
     const float* wres_blk;     // ... (and the residual 1x1 weights [chunk][N][32]): boxes come by 1-D bulk copy
     uint32_t idesc;
     int issuers2;              // single-CTA kernel: warps 1 and 2 each issue the MMAs of one half tile (SINDDM_TC_ISSUERS=1: warp 1 issues both)
+    int peek;                  // MMA warps test the next weight box's barrier inside the MMA asm, no per-box tcgen05 fence (SINDDM_TC_PEEK=0: off)
     int l2pf;                  // warp 3 prefetches the streamed epilogue operand into L2 one tile ahead (SINDDM_TC_L2PF=1)
     int dbg;                   // diagnostics (SINDDM_TC_DEBUG): 1 = no operand loads, 2 = no epilogue traffic, 4 = no MMAs, 8 = stage but do not store
     ConvEpilogue ep;
@@ -259,6 +260,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         uint32_t slot_uses[kSlots] = {0, 0, 0};
         int titer = 0;
         const uint32_t desc_hi = (uint32_t)(umma_smem_desc(0, 0, 1024, UMMA_LAYOUT_SW128) >> 32);
+        // Every barrier / tcgen05 bookkeeping instruction stalls this warp for 180-260 cycles (tools/pipe_bench.cu),
+        // about as long as the four N = 80 MMAs of a weight box execute.  So the NEXT box's full barrier is tested
+        // inside the asm that issues the current box's MMAs (the answer is read after the MMAs were issued;
+        // mbar_wait only when it was "not yet"), and there is no tcgen05.fence per box: operands written by TMA and
+        // observed through the mbarrier need none (the fence after the accumulator-slot wait orders against the
+        // epilogue's tcgen05.ld).  SINDDM_TC_PEEK=0 restores wait + fence per box.
+        bool b_ready = false;
         for (int st = pair_id; st < nsuper; st += npairs, ++titer) {
             const int s0 = (2 * titer) % kSlots, s1 = (2 * titer + 1) % kSlots;
             const int slot = half ? s1 : s0;
@@ -277,17 +285,26 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                 mbar_wait(&fulla_bar[sa_i], pha);
                 const uint32_t sa = smem_u32(smem + (size_t)sa_i * kABytes);
                 for (int ky = 0; ky < kys; ++ky) {
-                    mbar_wait(&fullb_bar[sb_i], phb);
-                    tc_fence_after_sync();
+                    if (!b_ready) mbar_wait(&fullb_bar[sb_i], phb);
+                    if (!a.peek) tc_fence_after_sync();
                     // vertical tap = row offset into the halo box; the 1x1 / residual case reads the centre rows
                     const int row0 = ((main && nky == 3) ? ky : 1) + 8 * half;
                     const uint32_t ad = ((sa + (uint32_t)row0 * kRowBytes) >> 4) & 0x3FFFu;
                     const uint32_t bd = (smem_u32(smem_b + (size_t)sb_i * a.bbox_bytes) >> 4) & 0x3FFFu;
-                    if (!(a.dbg & 4)) umma_tf32_ss_x4(dacc, ad, bd, desc_hi, 2u, a.idesc, (it | ky) != 0 ? 1u : 0u, nmma);
-                    umma_commit_elect(&emptyb_bar[sb_i]);
+                    const int sb_cur = sb_i;
                     if (++sb_i == a.nstages_b) {
                         sb_i = 0;
                         phb ^= 1u;
+                    }
+                    if (a.peek && !(a.dbg & 4)) {
+                        const uint32_t r = umma_tf32_ss_x4_test(dacc, ad, bd, desc_hi, 2u, a.idesc, (it | ky) != 0 ? 1u : 0u,
+                                                                nmma, &fullb_bar[sb_i], phb);
+                        umma_commit_elect(&emptyb_bar[sb_cur]);
+                        b_ready = __all_sync(0xffffffffu, r != 0);
+                    } else {
+                        if (!(a.dbg & 4)) umma_tf32_ss_x4(dacc, ad, bd, desc_hi, 2u, a.idesc, (it | ky) != 0 ? 1u : 0u, nmma);
+                        umma_commit_elect(&emptyb_bar[sb_cur]);
+                        b_ready = false;
                     }
                 }
                 umma_commit_elect(&emptya_bar[sa_i]);
@@ -766,6 +783,10 @@ int tc_conv_launch(const TcConvOp& op, cudaStream_t stream) {
     a.idesc = umma_idesc_tf32(op.cs == 2 ? 256 : 128, p.N, 0, 0);
     a.w_blk = p.w_blocked ? p.w : nullptr;
     a.wres_blk = p.w_blocked ? p.w_res : nullptr;
+    {
+        const char* e = getenv("SINDDM_TC_PEEK");
+        a.peek = e ? (atoi(e) != 0) : 1;
+    }
     {
         const char* e = getenv("SINDDM_TC_L2PF");    // measured neutral (profiles/): off unless asked for
         a.l2pf = e ? (atoi(e) != 0) : 0;
