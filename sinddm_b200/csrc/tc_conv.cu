@@ -545,8 +545,17 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                             pre2[q] = valid ? __ldg(reinterpret_cast<const float4*>(gsrc2 + pix * N + cc) + q)
                                             : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
+                    {   // s_bias is 16-byte aligned and cc a multiple of 16: four broadcast LDS.128 instead of sixteen LDS.32
+                        const float4* b4 = reinterpret_cast<const float4*>(s_bias + cc);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] += s_bias[cc + j];
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 bb = b4[q];
+                            v[4 * q + 0] += bb.x;
+                            v[4 * q + 1] += bb.y;
+                            v[4 * q + 2] += bb.z;
+                            v[4 * q + 3] += bb.w;
+                        }
+                    }
                     if (ep.w_res3) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {

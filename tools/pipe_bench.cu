@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(128, 1) bench(int mode, int N, int iters, int 
     const uint32_t hi = (uint32_t)(umma_smem_desc(0, 0, 1024, UMMA_LAYOUT_SW128) >> 32);
     const uint32_t idesc = umma_idesc_tf32(128, N, 0, 0);
     const uint32_t sa = smem_u32(smem), sb = sa + 48 * 1024;
-    if (warp == 1) {            // "MMA warp"
+    if (warp == 1 && mode < 7) {            // "MMA warp"
         if (mode == 1) {        // make phase 0 of full[0] complete once
             if ((threadIdx.x & 31) == 0) mbar_arrive(&full[0]);
             __syncwarp();
@@ -79,7 +79,35 @@ __global__ void __launch_bounds__(128, 1) bench(int mode, int N, int iters, int 
             out[0] = t1 - t0;
             out[1] = t_issue - t0;
         }
-    } else if (warp == 0 && mode >= 4) {   // "producer"
+    } else if (warp == 2 && mode >= 7) {   // "epilogue warp" primitives
+        const long long t0 = clock64();
+        for (int i = 0; i < iters; ++i) {
+            if (mode == 7) fence_proxy_async_smem();
+            else if (mode == 8) { if ((threadIdx.x & 31) == 0) bulk_wait_group_read<0>(); __syncwarp(); }
+            else if (mode == 9) { if ((threadIdx.x & 31) == 0) bulk_commit_group(); __syncwarp(); }
+            else if (mode == 10) __syncwarp();
+            else if (mode == 11) {      // the whole store sequence of one 2 KiB staging tile, without the TMA store itself
+                if ((threadIdx.x & 31) == 0) bulk_wait_group_read<1>();
+                __syncwarp();
+                *reinterpret_cast<float4*>(smem + (threadIdx.x & 31) * 64) = make_float4(1.f, 2.f, 3.f, 4.f);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if ((threadIdx.x & 31) == 0) bulk_commit_group();
+            } else if (mode == 12) {
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            } else if (mode == 13) {
+                uint32_t r[16];
+                tmem_ld16_issue(tm, r);
+                tmem_ld16_wait(r);
+                if (r[0] == 0x12345678u) out[3] = 1;
+            }
+        }
+        const long long t1 = clock64();
+        if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) {
+            out[0] = t1 - t0;
+            out[1] = t1 - t0;
+        }
+    } else if (warp == 0 && mode >= 4 && mode < 7) {   // "producer"
         int s = 0;
         uint32_t ph = 0;
         for (int i = 0; i < iters; ++i) {
@@ -103,15 +131,19 @@ int main() {
     long long* d;
     cudaMalloc(&d, 16);
     cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    const char* names[7] = {"commit only", "ready mbarrier wait only", "tcgen05.fence::after only", "x4 MMA + commit",
+    const char* names[14] = {"commit only", "ready mbarrier wait only", "tcgen05.fence::after only", "x4 MMA + commit",
                             "ring: wait + commit | wait + arrive", "ring: wait + x4 MMA + commit | wait + arrive",
-                            "ring: wait + plain arrive | wait + arrive"};
+                            "ring: wait + plain arrive | wait + arrive", "fence.proxy.async.shared::cta",
+                            "cp.async.bulk.wait_group.read 0 (nothing pending)", "cp.async.bulk.commit_group (empty)",
+                            "__syncwarp", "store sequence w/o TMA (wait_group, STS, fence, commit)", "tcgen05.wait::ld (nothing pending)",
+                            "tcgen05.ld x16 + wait"};
     const int iters = 4096;
-    for (int mode = 0; mode < 7; ++mode) {
+    cudaMalloc(&d, 64);
+    for (int mode = 0; mode < 14; ++mode) {
         for (int N : {80, 160}) {
             if (N == 160 && !(mode == 3 || mode == 5)) continue;
             for (int depth : {3, 4, 8}) {
-                if (mode < 4 && depth != 8) continue;
+                if ((mode < 4 || mode >= 7) && depth != 8) continue;
                 bench<<<148, 128, 100 * 1024>>>(mode, N, iters, depth, d);
                 cudaError_t e = cudaDeviceSynchronize();
                 long long both[2] = {0, 0};
