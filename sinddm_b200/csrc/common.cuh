@@ -92,6 +92,22 @@ SINDDM_DEVINL uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// 16-byte shared-memory accesses by shared-window address (no generic-pointer arithmetic in the hot loops)
+SINDDM_DEVINL void sts_f4(uint32_t addr, float x, float y, float z, float w) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+// ld.VOLATILE: `asm volatile` only pins the statement for the front end; to ptxas a plain ld.shared is an ordinary
+// load that it may sink towards its use or re-execute to save registers.  Tiles that the async proxy (TMA) overwrites
+// behind ptxas's back must be read exactly once, where the program says so.
+SINDDM_DEVINL float4 lds_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "r"(addr)
+                 : "memory");
+    return v;
+}
+
 // True in exactly one lane of a fully converged warp.  tcgen05.mma / TMA / tcgen05.commit are issued through
 // the uniform datapath: they must sit in WARP-UNIFORM control flow guarded by this predicate.  Guarding them
 // with `lane == 0` instead makes the compiler wrap each one in an ELECT/branch loop over the active lanes,

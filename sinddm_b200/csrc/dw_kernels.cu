@@ -416,6 +416,8 @@ dw5x5_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const float* __restr
             dw5x5_tile<ADD, ROUND, false, CSUM>(tile, ry, lane, wr, bv, cv, add, out, off, C, rowstride, W - w0, ok_a,
                                                     ok_b, csum);
         }
+        // generic-proxy reads of `buf` are followed by an async-proxy (TMA) refill: proxy fence, then the barrier
+        fence_proxy_async_smem();
         __syncthreads();   // everyone is done with `buf` before it is refilled
     }
     if (CSUM) {
@@ -521,6 +523,7 @@ dw5x5_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __
                     acc[ky][kx] = fmaf(win[ky + 1][(wo + kx) % 5], gb, fmaf(win[ky][(wo + kx) % 5], ga, acc[ky][kx]));
             }
         }
+        fence_proxy_async_smem();   // generic reads -> async-proxy refill (see the forward kernel)
         __syncthreads();   // everyone is done with `buf` before it is refilled two iterations later
     }
     // reduce over the 8 row pairs through shared memory (the tile buffers are free now)

@@ -457,6 +457,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         uint64_t* in_bar = &epi_in_bar[ew];
         // 64B swizzle: the 16-byte unit index of a row is XORed with bits 7-8 of the row's byte offset
         const uint32_t lrow = (uint32_t)lane * 64u, swz = (uint32_t)(lane >> 1) & 3u;
+        // shared-window addresses of this lane's four 16-byte units in staging tile 0 (tile 1 = + kEpiTileBytes)
+        const uint32_t stg_u32 = smem_u32(stg_in);
+        const uint32_t so0 = stg_u32 + lrow + ((0u ^ swz) << 4), so1 = stg_u32 + lrow + ((1u ^ swz) << 4);
+        const uint32_t so2 = stg_u32 + lrow + ((2u ^ swz) << 4), so3 = stg_u32 + lrow + ((3u ^ swz) << 4);
         uint32_t in_phase = 0;
         int obuf = 0;
         const float* gsrc = ep.res_add ? ep.res_add : ep.dgelu_z;   // streamed through TMA
@@ -506,10 +510,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                         else bulk_wait_group_read<1>();
                     }
                     __syncwarp();
-#pragma unroll
-                    for (uint32_t q = 0; q < 4; ++q)
-                        *reinterpret_cast<float4*>(buf + lrow + ((q ^ swz) << 4)) =
-                            make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    const uint32_t bo = (uint32_t)(buf - stg_in);
+                    sts_f4(so0 + bo, v[0], v[1], v[2], v[3]);
+                    sts_f4(so1 + bo, v[4], v[5], v[6], v[7]);
+                    sts_f4(so2 + bo, v[8], v[9], v[10], v[11]);
+                    sts_f4(so3 + bo, v[12], v[13], v[14], v[15]);
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0 && !(a.dbg & 8)) {
@@ -527,17 +532,28 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                     if (gsrc && live) {
                         mbar_wait(in_bar, in_phase);
                         in_phase ^= 1u;
-#pragma unroll
-                        for (uint32_t q = 0; q < 4; ++q)
-                            cur[q] = *reinterpret_cast<const float4*>(stg_in + lrow + ((q ^ swz) << 4));
-                        __syncwarp();
+                        cur[0] = lds_f4(so0);
+                        cur[1] = lds_f4(so1);
+                        cur[2] = lds_f4(so2);
+                        cur[3] = lds_f4(so3);
+                        // The next chunk's TMA load overwrites this tile (async proxy) right after these generic-proxy
+                        // reads.  Without a proxy fence between the two the hardware is free to perform the write first:
+                        // a few pixels then got the NEXT chunk's operand -- rare (<= 2 % of launches), timing dependent,
+                        // found by tools/determinism_stress.py (out = plain + res[c+32] exactly).  So: reads are
+                        // ld.volatile (ptxas may neither sink nor repeat them), every lane fences generic -> async, and
+                        // the warp vote on a predicate computed from the loaded registers (also the warp barrier) lets
+                        // lane 0 issue the load only after every lane's data has returned.
+                        fence_proxy_async_smem();
+                        {
+                            const uint32_t chk = __float_as_uint(cur[0].x) ^ __float_as_uint(cur[1].y) ^
+                                                 __float_as_uint(cur[2].z) ^ __float_as_uint(cur[3].w);
+                            const unsigned landed = __ballot_sync(0xffffffffu, chk != 0u);
+                            asm volatile("" ::"r"(landed) : "memory");
+                        }
                         if (lane == 0 && cc + 2 * kEpiChunk < N) {   // next chunk of this warp
                             mbar_arrive_expect_tx(in_bar, kEpiTileBytes);
                             tma_load_4d(stg_in, &tm_in, in_bar, cc + 2 * kEpiChunk, w0, hq, b);
                         }
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) cur[q] = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                     if (gsrc2) {
 #pragma unroll
