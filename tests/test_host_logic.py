@@ -204,3 +204,22 @@ def test_in_memory_pyramid_equals_the_png_round_trip(tmp_path):
         from_memory = MultiscaleTrainer(dif, None, pyramid=pyr, **kw)
         for (a0, a1), (b0, b1) in zip(from_files.data_list, from_memory.data_list):
             assert torch.equal(a0, b0) and torch.equal(a1, b1) and a0.shape[0] == 3
+
+
+def test_flattened_parameters_keep_the_module_surface():
+    """The fused optimizer step re-points every nn.Parameter at one flat buffer (fused_optim._flatten_params):
+    values, names, shapes and state_dict stay what they were, and the parameters alias the flat vector."""
+    from sinddm_b200.fused_optim import _flatten_params
+    net, _ = make(dim=16)
+    before = {k: v.clone() for k, v in net.state_dict().items()}
+    params = list(net.parameters())
+    flat = _flatten_params(params, 4)
+    assert flat.numel() % 4 == 0 and flat.numel() >= sum(p.numel() for p in params)
+    after = net.state_dict()
+    assert list(after) == list(before) and all(torch.equal(after[k], before[k]) for k in before)
+    off = 0
+    for p in params:
+        assert p.data_ptr() == flat.data_ptr() + 4 * off and p.is_contiguous()
+        off += p.numel()
+    flat.add_(1.0)                                    # a kernel writing the flat vector updates every parameter
+    assert all(torch.equal(net.state_dict()[k], before[k] + 1.0) for k in before)
