@@ -271,6 +271,8 @@ class MultiscaleTrainer(object):
             loss_backwards(self.fp16, loss / self.gradient_accumulate_every, self.opt)
         if fused is None:
             self.bucket.all_reduce_mean()
+        else:
+            self.model.denoise_fn.set_grad_bucket(None)     # manual backward calls outside the trainer keep `.grad`
         if self.step % self.avg_window == 0:
             acc = self._loss_acc.clone()
             if self.world > 1:
