@@ -7,9 +7,9 @@
 //                  N = output channels (one UMMA N, 16..160)
 //                  K = taps x input channels (+ an optional 1x1 residual conv as extra K from a second input)
 //
-// With fp32 (TF32) operands the kernel is bound by how many bytes the TMA unit can bring into shared memory
-// (measured ~32 B/cycle/SM, profiles/), not by the tensor pipe, so the K walk is arranged for operand reuse
-// INSIDE shared memory:
+// With fp32 (TF32) operands the wide layers are bound by the bytes that travel L2 -> shared memory (9 GB per
+// 160 -> 160 launch at 8.8 TB/s, ~85 % of the chip-wide limit; profiles/r01d_ncu_tc_conv.txt) before the tensor pipe
+// (76 % active), so the K walk is arranged for operand reuse INSIDE shared memory:
 //   * one pipeline stage = (32-channel chunk c, horizontal tap kx).  Its A box is the (16+2) x 16 pixel halo
 //     tile shifted by kx-1 columns (4-D TMA box (32 ch, 16 w, 18 h, 1 b); out-of-image pixels and the channel
 //     tail are zero-filled by TMA = exact zero padding, no im2col buffer).  The three vertical taps ky and
@@ -18,16 +18,24 @@
 //     so every loaded activation byte feeds 3 taps, and every weight byte (3 boxes [N][32] per stage) feeds
 //     256 pixels: 2.3x fewer bytes per FLOP than a tap-by-tap 128-pixel walk.
 //   * the halo boxes (36 KiB) and the weight boxes (N x 128 B, one per tap) travel through TWO independent
-//     mbarrier rings (3 activation slots, 5-8 weight slots), so ~200 KiB of loads stay in flight and the
-//     ~3000-cycle L2 latency is covered although one activation box feeds 24 MMAs.
+//     mbarrier rings (3 activation slots, 4-8 weight slots), so ~200 KiB of loads stay in flight and the
+//     L2 latency under load is covered although one activation box feeds 24 MMAs.
 //   * operands land in 128B-swizzled K-major tiles that the UMMA descriptors consume directly.
 //   accumulators   fp32 in TMEM: three slots of N columns; tile pair p uses slots (2p, 2p+1) mod 3, so the
 //                  main loop of pair p+1 only waits for the epilogue of the FIRST half of pair p.
 //   roles          (warpgroup aligned) warp 0: TMA producer | warp 1: TMEM alloc | warps 1 and 2: MMA issue, one per
 //                  M = 128 half of the tile (whole warps in uniform control flow, the issuing lane is elected inside
 //                  the asm: this removed a ~250-cycle/MMA issue cost; two issuers because one cannot feed N = 80)
-//                  warps 4-11: epilogue (TMEM -> registers -> bias/residual/GELU/... -> global), two warps per
-//                  TMEM lane quarter splitting the columns, global operands prefetched one chunk ahead
+//                  warp 3: optional L2 prefetcher of the streamed epilogue operand (off: measured neutral)
+//                  warps 4-11: epilogue (TMEM -> registers -> bias/residual/GELU/... -> smem tile -> TMA store), two
+//                  warps per TMEM lane quarter splitting the columns; a streamed operand (residual / saved gelu'(z))
+//                  arrives by TMA one chunk ahead.  The epilogue is bound by instruction issue, not latency: its
+//                  math is spelled out instruction by instruction (common.cuh), the forward pass saves gelu'(z) so
+//                  the data gradient only multiplies.
+//   barriers       every mbarrier wait / tcgen05.commit / tcgen05.fence costs its warp 150-260 cycles
+//                  (tools/pipe_bench.cu): waits are tested one box ahead inside the MMA asm, there is no per-box
+//                  tcgen05 fence, and generic <-> async proxy hand-overs of a shared-memory tile carry explicit
+//                  proxy fences in BOTH directions (the read -> TMA-refill direction was a real, rare race).
 //   grid           persistent, min(#tiles, #SMs) CTAs, static round-robin over tiles.
 #include <stdlib.h>
 #include <string.h>
