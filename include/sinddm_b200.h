@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SINDDM_ABI_VERSION 1
+#define SINDDM_ABI_VERSION 2
 
 typedef enum sinddm_status {
     SINDDM_STATUS_OK = 0,
@@ -216,6 +216,8 @@ typedef struct sinddm_fused_step_desc {
     long long step;              /* 1-based Adam step count t (bias corrections 1 - beta^t) */
     int ema_mode;                /* 0: none, 1: ema = param, 2: ema = ema * ema_beta + (1 - ema_beta) * param */
     float ema_beta;
+    unsigned long long* wait_ns; /* optional (NULL = off): device array of 2; [0] += nanoseconds this rank's first CTA
+                                  * spent in the NVLink barrier waiting for its peers (= rank skew), [1] = max of them */
 } sinddm_fused_step_desc;
 int sinddm_fused_step(const sinddm_fused_step_desc* desc, void* stream);
 

@@ -1,6 +1,7 @@
 """CPU oracle for the SinDDM hot path -- TEST INFRASTRUCTURE ONLY.
 
-A plain, functional restatement (torch CPU fp32/fp64 tensor ops, no nn.Module, no CUDA) of the reference
+A plain, functional restatement (stock torch fp32/fp64 tensor ops, no nn.Module, none of this repo's kernels; it
+follows its inputs' device, so bench.py can also time it as "the reference's eager PyTorch path on the GPU") of the reference
 algorithm on the path BASELINE.json names: the denoiser forward (SinDDMNet), the training loss
 (MultiScaleGaussianDiffusion.p_losses) with gradients by autograd of this restatement, the diffusion schedule
 and the reverse-sampling update (p_sample).  Every function cites the reference file:line it follows
@@ -117,7 +118,7 @@ def conv_block(p: Params, name: str, x: torch.Tensor, cond_vec: torch.Tensor) ->
 def net_forward(p: Params, x: torch.Tensor, time: torch.Tensor, scale) -> torch.Tensor:
     """SinDDMNet.forward (multiscale=True), SinDDM/models.py:134-151."""
     dtype = x.dtype
-    scale_tensor = torch.ones(time.shape, dtype=dtype) * float(scale)                                     # :137
+    scale_tensor = torch.ones(time.shape, dtype=dtype, device=x.device) * float(scale)                    # :137
     t = sinusoidal_pos_emb(time.to(dtype) if dtype == torch.float64 else time, 32).to(dtype)              # :138
     s = sinusoidal_pos_emb(scale_tensor, 32).to(dtype)                                                    # :139
     ts = torch.cat((t, s), dim=1)                                                                         # :140
@@ -176,6 +177,12 @@ class Schedule:
         for i in range(n_scales - 1):
             gammas[i, :] = (torch.tensor(sigma_t) / (loss_factor * scale_losses[i])).clamp(min=0, max=1)
         self.gammas = gammas
+
+    def to(self, device) -> "Schedule":
+        """Moves the tables (bench.py's reference-on-GPU eager baseline runs this restatement on `cuda`)."""
+        for n in list(self.buffers()):
+            setattr(self, n, getattr(self, n).to(device))
+        return self
 
     def buffers(self) -> Dict[str, torch.Tensor]:
         names = ["betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_alphas_cumprod",
@@ -260,7 +267,7 @@ def p_sample_update(sch: Schedule, x, eps, t, s: int, noise, x_tilde=None, reblu
         logvar = extract(sch.posterior_log_variance_clipped, t, shape)
     elif t[0] > 0:
         var_hi = 1 - extract(sch.alphas_cumprod, t - 1, shape)
-        var = (1 - omega) * torch.zeros(shape, dtype=x.dtype) + omega * var_hi
+        var = (1 - omega) * torch.zeros(shape, dtype=x.dtype, device=x.device) + omega * var_hi
         logvar = torch.log(var.clamp(1e-20, None))
         mean = (extract(sch.sqrt_alphas_cumprod, t - 1, shape) * x_tm1_mix +
                 torch.sqrt(1 - extract(sch.alphas_cumprod, t - 1, shape) - var) *

@@ -63,7 +63,7 @@ class FusedStepDesc(C.Structure):
         ("epoch", C.c_uint32),
         ("param", _vp), ("exp_avg", _vp), ("exp_avg_sq", _vp), ("ema", _vp),
         ("lr", _f), ("beta1", _f), ("beta2", _f), ("eps", _f),
-        ("step", _ll), ("ema_mode", _i), ("ema_beta", _f),
+        ("step", _ll), ("ema_mode", _i), ("ema_beta", _f), ("wait_ns", _vp),
     ]
 
 
@@ -126,7 +126,7 @@ def load():
             fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
             fn.restype = res
             fn.argtypes = args
-        if lib.sinddm_abi_version() != 1:
+        if lib.sinddm_abi_version() != 2:
             raise SinddmError("libsinddm_b200.so ABI version mismatch")
         _lib = lib
     return _lib

@@ -253,6 +253,7 @@ int sinddm_fused_step(const sinddm_fused_step_desc* d, void* stream) {
     a.step_size = (float)((double)d->lr / bc1);
     a.bias2_sqrt = (float)sqrt(bc2);
     a.ema_mode = d->ema_mode; a.ema_beta = d->ema_beta;
+    a.wait_ns = d->wait_ns;
     return fused_step_launch(a, as_stream(stream));
 }
 

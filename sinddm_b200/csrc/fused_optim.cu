@@ -40,6 +40,12 @@ SINDDM_DEVINL float4 ld_peer_f4(const float* p) {
     return v;
 }
 
+SINDDM_DEVINL unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 struct Args {
     FusedStepDesc d;
 };
@@ -63,12 +69,20 @@ __global__ void __launch_bounds__(256) fused_allreduce_adam_ema_kernel(const Arg
             __threadfence_system();
             st_release_sys(d.flags[threadIdx.x] + rank, d.epoch);      // flags[dst][src]
         }
+        unsigned long long t0 = 0;
+        if (d.wait_ns && blockIdx.x == 0 && threadIdx.x == 0) t0 = global_timer_ns();
         if ((int)threadIdx.x < world && (int)threadIdx.x != rank) {
             const uint32_t* f = d.flags[rank] + threadIdx.x;
             while ((int32_t)(ld_acquire_sys(f) - d.epoch) < 0) {
             }
         }
         __syncthreads();
+        if (d.wait_ns && blockIdx.x == 0 && threadIdx.x == 0) {
+            // how long this rank sat in the barrier = how far behind the slowest peer was (rank skew, not link time)
+            const unsigned long long dt = global_timer_ns() - t0;
+            d.wait_ns[0] += dt;
+            if (dt > d.wait_ns[1]) d.wait_ns[1] = dt;
+        }
     }
     const float inv_world = 1.f / (float)world;
     const long long n4 = d.n / 4;

@@ -22,6 +22,7 @@ struct FusedStepDesc {
     float bias2_sqrt;                      // sqrt(1 - beta2^t)
     int ema_mode;                          // 0: leave, 1: ema = param, 2: ema = ema * beta + (1 - beta) * param
     float ema_beta;
+    unsigned long long* wait_ns;           // optional: [0] += ns CTA 0 waited in the barrier, [1] = max (rank skew)
 };
 
 int fused_step_launch(const FusedStepDesc& d, cudaStream_t stream);

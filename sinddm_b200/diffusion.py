@@ -49,6 +49,11 @@ class EMA:
     def update_model_average(self, ma_model, current_model):
         for cur, ma in zip(current_model.parameters(), ma_model.parameters()):
             ma.data = self.update_average(ma.data, cur.data)
+        # rebinding `.data` changes neither the parameter's version counter nor, reliably, its address (the caching
+        # allocator recycles blocks): tell the CUDA plans that their packed copies of these weights are stale
+        net = getattr(ma_model, 'denoise_fn', ma_model)
+        if hasattr(net, 'mark_weights_updated'):
+            net.mark_weights_updated()
 
 
 class _L1LossFn(torch.autograd.Function):
@@ -260,6 +265,8 @@ class MultiScaleGaussianDiffusion(nn.Module):
         b, c, h, w = x_orig.shape
         img_size = self.image_sizes[s]
         assert h == img_size[0] and w == img_size[1], f'height and width of image must be {img_size}'
+        if not 0 < self.num_timesteps_trained[s] <= self.num_timesteps:
+            raise IndexError(f'num_timesteps_trained[{s}] = {self.num_timesteps_trained[s]} is outside the schedule')
         t = torch.randint(0, self.num_timesteps_trained[s], (b * self.dp_world,), device=x_orig.device).long()
         if self.dp_world > 1:
             t = self._shard(t, b)
@@ -380,6 +387,10 @@ class MultiScaleGaussianDiffusion(nn.Module):
         device = self.betas.device
         total_t = self.num_timesteps_ideal[min(s, self.n_scales - 1)] - 1 if custom_t is None else custom_t
         b = batch_size
+        # the kernels index the schedule / gamma tables with t and t-1 unchecked; the reference's gather raises for
+        # the same input (custom_t, --sample_t_list, --start_t_style, --start_t_harm)
+        if not 0 <= int(total_t) < self.num_timesteps:
+            raise IndexError(f'start timestep {total_t} is outside the schedule [0, {self.num_timesteps})')
         self.img_prev_upsample = img
         img = self.q_sample(x_start=img, t=torch.Tensor.expand(torch.tensor(total_t, device=device), batch_size),
                             noise=None)

@@ -85,6 +85,8 @@ class FusedStep:
             self.handle = None
             self.peer_ptrs = [self.symm.data_ptr()]
         self._sizes = [p.numel() for p in self.params]
+        # [0]: nanoseconds spent waiting for peers in the in-kernel barrier, summed over steps; [1]: the largest wait
+        self.wait_ns = torch.zeros(2, dtype=torch.int64, device=dev) if self.world > 1 else None
         for m in (net, ema_net):
             if m is not None and hasattr(m, "mark_weights_updated"):
                 m.mark_weights_updated()
@@ -97,6 +99,15 @@ class FusedStep:
     def grad_views(self) -> List[torch.Tensor]:
         """Per-parameter views of the current bucket (tests / debugging)."""
         return [v.view_as(p) for v, p in zip(self.bucket().split(self._sizes), self.params)]
+
+    def barrier_wait_ms(self, reset: bool = True):
+        """(total, max) milliseconds this rank spent in the fused step's NVLink barrier waiting for slower peers."""
+        if self.wait_ns is None:
+            return 0.0, 0.0
+        tot, mx = (float(v) * 1e-6 for v in self.wait_ns.tolist())
+        if reset:
+            self.wait_ns.zero_()
+        return tot, mx
 
     def step(self, lr: float, ema_mode: int = 0, ema_beta: float = 0.995) -> None:
         """Consumes the current bucket: mean over ranks, Adam, EMA.  Switches to the other bucket."""
@@ -116,6 +127,7 @@ class FusedStep:
         d.step = self.t
         d.ema_mode = int(ema_mode) if self.flat_ema is not None else 0
         d.ema_beta = float(ema_beta)
+        d.wait_ns = self.wait_ns.data_ptr() if self.wait_ns is not None else None
         stream = torch.cuda.current_stream(self.device).cuda_stream
         check(lib.sinddm_fused_step(C.byref(d), stream), "sinddm_fused_step")
         # the kernels wrote the parameters behind autograd's back: invalidate the packed conv weights

@@ -73,7 +73,7 @@ class MultiscaleTrainer(object):
                  image_sizes=None, train_batch_size=32, train_lr=2e-5, train_num_steps=100000,
                  gradient_accumulate_every=2, fp16=False, step_start_ema=2000, update_ema_every=10,
                  save_and_sample_every=25000, avg_window=100, sched_milestones=None, results_folder='./results',
-                 device=None, scale_draw='device', pyramid=None):
+                 device=None, scale_draw='device', pyramid=None, host_data=False, loss_readback='window'):
         super().__init__()
         self.device = device
         self.sched_milestones = [10000, 30000, 60000, 80000, 90000] if sched_milestones is None else sched_milestones
@@ -86,10 +86,21 @@ class MultiscaleTrainer(object):
         self.save_and_sample_every = save_and_sample_every
         self.avg_window = avg_window
 
-        # 'device': torch.multinomial on the device like the reference (trainer.py:197; same RNG stream, but the
-        # call costs ~6.6 ms of host time per step on a B200 box, profiles/); 'host': the same uniform draw from a
-        # CPU generator (microseconds; the device stream of t / noise then differs from the reference's)
+        # 'device': torch.multinomial on the device like the reference (trainer.py:197; same RNG stream).  The call
+        # validates its input with host read-backs, i.e. it synchronises the stream it runs on: issued on the
+        # training stream it drained the whole previous step before the next one could be enqueued (6 ms per step in
+        # round 1).  It now runs on a side stream (_draw_scale): same generator, same Philox offsets, same values, but
+        # the syncs only wait for the draw itself.  'host': the same uniform draw from a CPU generator (the device
+        # stream of t / noise then differs from the reference's)
         self.scale_draw = scale_draw
+        # host_data: keep data_list in pinned HOST memory and copy the step's batch in every step (the reference keeps
+        # it on the device, trainer.py:120-132; bench.py's end-to-end leg uses this).  loss_readback: 'window' reads
+        # the loss back once per avg_window; 'step' does the reference's loss.item() per micro-step (trainer.py:202)
+        self.host_data = bool(host_data)
+        if loss_readback not in ('window', 'step'):
+            raise ValueError("loss_readback must be 'window' or 'step'")
+        self.loss_readback = loss_readback
+        self.last_loss = None
         self.batch_size = train_batch_size           # GLOBAL batch (split over ranks under torchrun)
         self.n_scales = n_scales
         self.scale_factor = scale_factor
@@ -122,17 +133,17 @@ class MultiscaleTrainer(object):
                 self.ds_list.append(None)
                 orig = _to_model_range(level).unsqueeze(0).repeat(n, 1, 1, 1)
                 other = _to_model_range(blurry).unsqueeze(0).repeat(n, 1, 1, 1) if i > 0 else orig.clone()
-                self.data_list.append((orig.to(self.device), other.to(self.device)))
+                self.data_list.append((self._place(orig), self._place(other)))
         for i in range(n_scales if pyramid is None else 0):
             self.input_paths.append(folder + 'scale_' + str(i))
             ds = Dataset(self.input_paths[i], image_sizes[i] if i < len(image_sizes) else None, blurry_img=i > 0)
             self.ds_list.append(ds)
             if i > 0:
                 orig, blur = ds.batch(self.local_batch)
-                self.data_list.append((orig.to(self.device), blur.to(self.device)))
+                self.data_list.append((self._place(orig), self._place(blur)))
             else:
                 orig = ds.batch(self.local_batch)
-                self.data_list.append((orig.to(self.device), orig.clone().to(self.device)))
+                self.data_list.append((self._place(orig), self._place(orig.clone())))
 
         self.opt = Adam(ms_diffusion_model.parameters(), lr=train_lr)
         self.scheduler = MultiStepLR(self.opt, milestones=self.sched_milestones, gamma=0.5)
@@ -143,14 +154,50 @@ class MultiscaleTrainer(object):
         self.running_loss = []
         self.running_scale = []
         self.avg_t = []
+        self.scale_counts = [0] * (n_scales or 0)      # new: how often train_step ran each scale
+        self._copy_stream = None
 
         assert not fp16, 'Apex must be installed in order for mixed precision training to be turned on'
         self.fp16 = fp16
         self.reset_parameters()
 
     # ---------------------------------------------------------------------------------------------
+    def _place(self, batch):
+        """Where a scale's training batch lives between steps: on the device (reference behaviour) or, with
+        host_data=True, in pinned host memory from which every step copies it in."""
+        if self.host_data:
+            return batch.contiguous().pin_memory() if torch.cuda.is_available() else batch.contiguous()
+        return batch.to(self.device)
+
+    def _batch(self, s):
+        pair = self.data_list[s]
+        if not self.host_data:
+            return pair
+        if not pair[0].is_pinned():
+            return tuple(t.to(self.device) for t in pair)
+        # copy on a side stream: the transfer overlaps the previous step's kernels still queued on the training
+        # stream, which only waits for the copy's completion event
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        main = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self._copy_stream):
+            out = tuple(t.to(self.device, non_blocking=True) for t in pair)
+        main.wait_stream(self._copy_stream)
+        for t in out:
+            t.record_stream(main)
+        return out
+
     def reset_parameters(self):
         self.ema_model.load_state_dict(self.model.state_dict())
+        self._ema_weights_changed()
+
+    def _ema_weights_changed(self):
+        """The EMA copy's parameters were rewritten (load_state_dict copies in place, EMA.update_model_average
+        rebinds `.data`): neither is guaranteed to change (data_ptr, _version), the key the packed conv weights are
+        cached under, so say it explicitly (stale packed weights in ema_model.sample)."""
+        net = getattr(self.ema_model, 'denoise_fn', None)
+        if net is not None and hasattr(net, 'mark_weights_updated'):
+            net.mark_weights_updated()
 
     def step_ema(self):
         """trainer.py:155-159: hard copy until step_start_ema, EMA afterwards (quirk Q8)."""
@@ -158,6 +205,7 @@ class MultiscaleTrainer(object):
             self.reset_parameters()
             return
         self.ema.update_model_average(self.ema_model, self.model)
+        self._ema_weights_changed()
 
     def save(self, milestone):
         """trainer.py:161-177 (rank 0 only; the loss plot needs matplotlib and is skipped when it is absent)."""
@@ -194,6 +242,10 @@ class MultiscaleTrainer(object):
         self.ema_model.load_state_dict(ckpt['ema'])
         self.scheduler.load_state_dict(ckpt['sched'])
         self.running_loss = ckpt['running_loss']
+        for m in (self.model, self.ema_model):      # packed conv weights are rebuilt from the loaded parameters
+            net = getattr(m, 'denoise_fn', None)
+            if net is not None and hasattr(net, 'mark_weights_updated'):
+                net.mark_weights_updated()
         opt_path = self.results_folder / f'optim-{milestone}.pt'
         if opt_path.exists():       # absent for checkpoints written by the reference: Adam restarts, like there
             self._set_optimizer_state(torch.load(str(opt_path), map_location='cpu'))
@@ -251,30 +303,48 @@ class MultiscaleTrainer(object):
                                  'exp_avg_sq': v.view_as(p).to(p.device).clone()}
 
     # ---------------------------------------------------------------------------------------------
+    def _draw_scale(self):
+        """trainer.py:197: s ~ multinomial(num_timesteps_trained) from the device generator.  torch.multinomial checks
+        its weights with host read-backs (stream synchronisations), so it runs on a side stream: the values depend on
+        the generator's Philox offset, which advances at call time on the host, not on the stream -- the draw is the
+        one the reference makes, but the training stream is not drained and the host keeps running ahead."""
+        if self.scale_draw == 'host':
+            return int(torch.multinomial(input=self._s_weights_host, num_samples=1, generator=self._host_gen))
+        if self._draw_stream is None:
+            return int(torch.multinomial(input=self._s_weights, num_samples=1))
+        with torch.cuda.stream(self._draw_stream):
+            return int(torch.multinomial(input=self._s_weights, num_samples=1))
+
     def train_step(self, s=None):
         """One optimizer step (trainer.py:196-214).  Returns the (device, fp32) loss of the last micro-batch."""
-        if s is None:
-            if self.scale_draw == 'host':
-                s = torch.multinomial(input=self._s_weights_host, num_samples=1, generator=self._host_gen)
-            else:
-                s = torch.multinomial(input=self._s_weights, num_samples=1)
-        s = int(s)                                        # the reference syncs here too (list index by tensor)
+        s = self._draw_scale() if s is None else int(s)
+        if s < len(self.scale_counts):
+            self.scale_counts[s] += 1
         loss = None
         fused = self._fused
         if fused is not None:
             # backward writes the 52 gradients straight into this step's (peer-mapped) bucket
             self.model.denoise_fn.set_grad_bucket(fused.bucket())
         for _ in range(self.gradient_accumulate_every):
-            batch = self.data_list[s]
+            batch = self._batch(s)
             loss = self.model(batch, s)
-            self._loss_acc += loss.detach().double()
+            if self.loss_readback == 'step':
+                self.last_loss = loss.item()                # the reference's per-micro-step host sync (trainer.py:202)
+                self._loss_acc_host += self.last_loss
+            else:
+                self._loss_acc += loss.detach().double()
             loss_backwards(self.fp16, loss / self.gradient_accumulate_every, self.opt)
         if fused is None:
             self.bucket.all_reduce_mean()
         else:
             self.model.denoise_fn.set_grad_bucket(None)     # manual backward calls outside the trainer keep `.grad`
         if self.step % self.avg_window == 0:
-            acc = self._loss_acc.clone()
+            if self.loss_readback == 'step':
+                acc = torch.tensor(self._loss_acc_host, dtype=torch.float64, device=self.device)
+                self._loss_acc_host = 0.0
+            else:
+                acc = self._loss_acc.clone()
+                self._loss_acc.zero_()
             if self.world > 1:
                 import torch.distributed as tdist
                 tdist.all_reduce(acc)
@@ -283,7 +353,6 @@ class MultiscaleTrainer(object):
             if self.rank == 0:
                 print(f'step:{self.step} loss:{avg}')
             self.running_loss.append(avg)
-            self._loss_acc.zero_()
         if fused is not None:
             # one kernel: gradient mean over the ranks (NVLink peer loads), Adam, EMA (trainer.py:208-213)
             ema_mode = 0
@@ -301,31 +370,97 @@ class MultiscaleTrainer(object):
 
     def _make_fused_step(self):
         """The fused all-reduce + Adam + EMA step (sinddm_b200.fused_optim) when the configuration allows it:
-        CUDA, one micro-batch per optimizer step, SINDDM_FUSED_STEP != 0.  Otherwise torch.optim.Adam + NCCL."""
+        CUDA, one micro-batch per optimizer step, at most FUSED_MAX_WORLD ranks, SINDDM_FUSED_STEP != 0.  Otherwise
+        (and when its construction fails on ANY rank: no peer access, symmetric-memory rendezvous refused)
+        torch.optim.Adam + the NCCL bucket.  The decision is agreed across ranks."""
         import os
+        import warnings
+
+        from . import _capi
         net = getattr(self.model, 'denoise_fn', None)
         ok = (os.environ.get('SINDDM_FUSED_STEP', '1') != '0' and self.gradient_accumulate_every == 1
               and net is not None and hasattr(net, 'set_grad_bucket')
-              and next(net.parameters()).is_cuda)
-        if not ok:
-            return None
-        from .fused_optim import FusedStep
-        group = self.opt.param_groups[0]
-        fused = FusedStep(net, self.ema_model.denoise_fn, betas=group['betas'], eps=group['eps'])
-        self.opt._opt_called = True      # the scheduler only reads the learning rate from this optimizer now
+              and next(net.parameters()).is_cuda and self.world <= _capi.FUSED_MAX_WORLD)
+        fused, why = None, ''
+        if ok:
+            try:
+                from .fused_optim import FusedStep
+                group = self.opt.param_groups[0]
+                fused = FusedStep(net, self.ema_model.denoise_fn, betas=group['betas'], eps=group['eps'])
+            except Exception as e:      # noqa: BLE001 -- any failure means "use the fallback", on every rank
+                fused, why = None, f'{type(e).__name__}: {e}'
+        if self.world > 1:
+            import torch.distributed as tdist
+            flag = torch.tensor([1 if fused is not None else 0], dtype=torch.int32,
+                                device=self.device if tdist.get_backend() == 'nccl' else 'cpu')
+            tdist.all_reduce(flag, op=tdist.ReduceOp.MIN)
+            if int(flag.item()) == 0 and fused is not None:
+                fused, why = None, 'another rank could not build the fused step'
+        if ok and fused is None:
+            warnings.warn(f'sinddm_b200: fused optimizer step unavailable ({why}); using NCCL all-reduce + torch.optim.Adam')
+            # FusedStep may have re-pointed the parameters at its flat buffers before failing: values are intact
+        if fused is not None:
+            self.opt._opt_called = True      # the scheduler only reads the learning rate from this optimizer now
         return fused
 
+    def _sync_replicas(self):
+        """Data-parallel start: every rank must hold bit-identical parameters, EMA parameters and RNG state, because
+        nothing re-synchronises the replicas later (the fused step applies the same update everywhere) and the scale
+        draw / global (t, noise) stream come from each rank's own generator.  Rank 0's state wins."""
+        if self.world <= 1:
+            return
+        import torch.distributed as tdist
+        on_gpu = tdist.get_backend() == 'nccl'
+        with torch.no_grad():
+            for m in (self.model, self.ema_model):
+                for p in m.parameters():
+                    tdist.broadcast(p.data, src=0)
+                for b in m.buffers():
+                    tdist.broadcast(b.data, src=0)
+        for m in (self.model, self.ema_model):
+            net = getattr(m, 'denoise_fn', None)
+            if net is not None and hasattr(net, 'mark_weights_updated'):
+                net.mark_weights_updated()
+        cpu_state = torch.get_rng_state()
+        st = cpu_state.to(self.device) if on_gpu else cpu_state.clone()
+        tdist.broadcast(st, src=0)
+        torch.set_rng_state(st.cpu())
+        if on_gpu:
+            st = torch.cuda.get_rng_state(self.device).to(self.device)
+            tdist.broadcast(st, src=0)
+            torch.cuda.set_rng_state(st.cpu(), self.device)
+
     def _prepare_training(self):
+        if not getattr(self, '_replicas_synced', False):
+            self._sync_replicas()
+            self._replicas_synced = True
         if self._fused is None and not getattr(self, '_fused_decided', False):
             self._fused = self._make_fused_step()
             self._fused_decided = True
             self._apply_optimizer_state()      # state loaded before the optimizer implementation was chosen
         self._s_weights = torch.tensor(self.model.num_timesteps_trained, device=self.device, dtype=torch.float)
         self._s_weights_host = self._s_weights.cpu()
+        on_cuda = self._s_weights.is_cuda
+        if on_cuda:
+            torch.cuda.current_stream(self._s_weights.device).synchronize()     # weights visible to the side stream
+        if not hasattr(self, '_draw_stream'):
+            self._draw_stream = torch.cuda.Stream(device=self._s_weights.device) if on_cuda else None
         if not hasattr(self, '_host_gen'):
             self._host_gen = torch.Generator().manual_seed(torch.initial_seed() % (2 ** 63))
         if not hasattr(self, '_loss_acc'):
             self._loss_acc = torch.zeros((), dtype=torch.float64, device=self.device)
+            self._loss_acc_host = 0.0
+
+    def _gather_images(self, local):
+        """Rank-ordered concatenation of every rank's image shard (the global noise stream is sharded in rank order,
+        so this is the batch one GPU would have produced).  Collective: every rank must call it; the result is
+        complete on every rank."""
+        if self.world <= 1:
+            return local
+        import torch.distributed as tdist
+        parts = [torch.empty_like(local) for _ in range(self.world)]
+        tdist.all_gather(parts, local.contiguous())
+        return torch.cat(parts, dim=0)
 
     def train(self):
         self._prepare_training()
@@ -334,7 +469,16 @@ class MultiscaleTrainer(object):
             if self.step % self.save_and_sample_every == 0:
                 milestone = self.step // self.save_and_sample_every
                 batches = num_to_groups(16, self.batch_size)
-                images = torch.cat([self.ema_model.sample(batch_size=n) for n in batches], dim=0)
+                shard = all(n % self.world == 0 for n in batches)     # else every rank samples the whole group
+                if not shard:
+                    self.ema_model.set_data_parallel(0, 1)
+                try:
+                    images = torch.cat([self.ema_model.sample(batch_size=n // self.world if shard else n)
+                                        for n in batches], dim=0)
+                finally:
+                    self.ema_model.set_data_parallel(self.rank, self.world)
+                if shard:
+                    images = self._gather_images(images)
                 images = (images + 1) * 0.5
                 if self.rank == 0:
                     from torchvision import utils
@@ -348,8 +492,9 @@ class MultiscaleTrainer(object):
                       custom_scales=None, image_name='', start_noise=True, custom_t_list=None, desc=None,
                       save_unbatched=True, save_images=True):
         """trainer.py:226-285: coarse-to-fine sampling driver, always on the EMA model.  Under torchrun each
-        rank generates batch_size / world_size images (no collective).  Returns the list of per-scale
-        batches; `save_images=False` skips the PNG writes (benchmarks)."""
+        rank generates batch_size / world_size images with no collective on the sampling path; when images are
+        written, the shards are gathered (rank order = the 1-GPU batch order) and rank 0 writes all batch_size of
+        them.  Returns the list of per-scale batches of THIS rank; `save_images=False` skips gather and PNG writes."""
         ema = self.ema_model
         if desc is None:
             desc = f'sample_{str(datetime.datetime.now()).replace(":", "_")}'
@@ -392,6 +537,8 @@ class MultiscaleTrainer(object):
                                                     custom_img_size_idx=custom_image_size_idxs[i],
                                                     custom_t=custom_t_list[int(custom_scales[i]) - 1]))
             final_img = (samples[i] + 1) * 0.5
+            if save_images:
+                final_img = self._gather_images(final_img)
             if save_images and self.rank == 0:
                 from torchvision import utils
                 utils.save_image(final_img, str(out_dir / prefix) +

@@ -52,6 +52,27 @@ def _worker(rank, world, port, out_dir):
     assert spdist.shard_batch(32, world) == 16
     with pytest.raises(ValueError):
         spdist.shard_batch(33, world)
+    # --- trainer start-up: rank 0's parameters / EMA / RNG state win, image shards gather in rank order
+    import numpy as np
+    from PIL import Image
+    from sinddm_b200 import MultiscaleTrainer
+    torch.manual_seed(1000 + rank)                      # replicas deliberately different
+    net2 = SinDDMNet(dim=16, multiscale=True)
+    dif2 = MultiScaleGaussianDiffusion(denoise_fn=net2, n_scales=2, scale_factor=1.3, image_sizes=GOLDEN_SIZES[:2],
+                                       timesteps=100, train_full_t=True, scale_losses=GOLDEN_SCALE_LOSSES[:1],
+                                       results_folder=tempfile.mkdtemp())
+    pyr = [(Image.fromarray(np.full((h, w, 3), 40 * (i + 1), np.uint8)),) * 2 for i, (w, h) in enumerate(GOLDEN_SIZES[:2])]
+    tr = MultiscaleTrainer(dif2, None, n_scales=2, image_sizes=GOLDEN_SIZES[:2], train_batch_size=4,
+                           results_folder=tempfile.mkdtemp(), device="cpu", pyramid=pyr)
+    assert tr.local_batch == 2 and tr.data_list[1][0].shape[0] == 2
+    tr._sync_replicas()
+    flat = torch.cat([p.detach().reshape(-1) for p in tr.model.parameters()] +
+                     [p.detach().reshape(-1) for p in tr.ema_model.parameters()] + [torch.rand(4)])
+    both = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(both, flat)
+    assert torch.equal(both[0], both[1]), "replicas / RNG differ after _sync_replicas"
+    imgs = tr._gather_images(torch.full((2, 3, 4, 5), float(rank)))
+    assert imgs.shape[0] == 4 and torch.equal(imgs[:2], torch.zeros(2, 3, 4, 5)) and torch.equal(imgs[2:], torch.ones(2, 3, 4, 5))
     dist.barrier()
     dist.destroy_process_group()
 

@@ -113,3 +113,104 @@ def test_harmonization_and_style_transfer_modes(tmp_path):
     far[0:80, 10:100] = False                                 # > 7 px dilation + 4 sigma of blur away from the mask
     assert np.abs(h[far] - comp.astype(int)[far]).max() <= 1  # untouched outside the mask (8-bit rounding)
     assert np.abs(h[35:45, 45:65] - comp.astype(int)[35:45, 45:65]).max() > 1
+
+
+def _small_trainer(tmp_path, **kw):
+    from sinddm_b200 import MultiScaleGaussianDiffusion, MultiscaleTrainer, SinDDMNet, create_img_scales
+    ds = str(tmp_path / "data") + "/"
+    if not os.path.exists(ds):
+        _image(ds)
+    sizes, losses, sf, ns = create_img_scales(ds, "synth.png", scale_factor=1.411, create=True, auto_scale=50000)
+    dev = "cuda:0"
+    net = SinDDMNet(dim=160, multiscale=True, device=dev).to(dev)
+    dif = MultiScaleGaussianDiffusion(denoise_fn=net, n_scales=ns, scale_factor=sf, image_sizes=sizes, timesteps=100,
+                                      train_full_t=True, scale_losses=losses, device=dev,
+                                      results_folder=str(tmp_path / "r")).to(dev)
+    args = dict(n_scales=ns, scale_factor=sf, image_sizes=sizes, train_batch_size=4, train_lr=1e-3,
+                train_num_steps=10 ** 9, gradient_accumulate_every=1, step_start_ema=2, update_ema_every=1,
+                save_and_sample_every=10 ** 9, avg_window=10 ** 9, results_folder=str(tmp_path / "r"), device=dev)
+    args.update(kw)
+    return MultiscaleTrainer(dif, ds, **args), (sizes, losses, sf, ns)
+
+
+def test_side_stream_scale_draw_keeps_the_reference_rng_stream(tmp_path):
+    """trainer.py:197 draws s with torch.multinomial from the device generator between the previous step's randn and
+    this step's randint (quirk Q7).  The trainer issues that call on a side stream (no drain of the training stream);
+    the values -- s, and the t / noise drawn after it, visible through the loss -- must be those of the plain
+    in-stream call."""
+    seqs, losses = [], []
+    for side in (True, False):
+        torch.manual_seed(11)
+        tr, _ = _small_trainer(tmp_path)
+        tr._prepare_training()
+        if not side:
+            tr._draw_stream = None                      # plain torch.multinomial on the training stream
+        seq = []
+        draw = tr._draw_scale
+        tr._draw_scale = lambda draw=draw, seq=seq: (seq.append(draw()) or seq[-1])
+        torch.manual_seed(5)
+        ls = [float(tr.train_step()) for _ in range(8)]
+        seqs.append(seq)
+        losses.append(ls)
+    assert seqs[0] == seqs[1] and len(set(seqs[0])) > 1, seqs
+    assert losses[0] == losses[1], losses               # same t, same noise, same kernels: bit-identical
+
+
+def test_host_data_and_per_step_loss_readback_match_the_device_resident_path(tmp_path):
+    """host_data=True (batch copied in from pinned memory on a side stream every step) and loss_readback='step' (the
+    reference's loss.item() per step) change where the bytes live, not the numbers."""
+    out = []
+    for host in (False, True):
+        torch.manual_seed(3)
+        tr, _ = _small_trainer(tmp_path, host_data=host, loss_readback="step" if host else "window", avg_window=4)
+        tr.train_num_steps = 8
+        torch.manual_seed(9)
+        tr.train()
+        assert tr.step == 8 and sum(tr.scale_counts) == 8
+        if host:
+            assert all(t.is_pinned() and not t.is_cuda for pair in tr.data_list for t in pair)
+            assert isinstance(tr.last_loss, float)
+        out.append(([p.detach().clone() for p in tr.model.parameters()], list(tr.running_loss)))
+    for a, b in zip(out[0][0], out[1][0]):
+        assert torch.equal(a, b)
+    assert np.allclose(out[0][1], out[1][1], rtol=1e-6)
+
+
+def test_ema_sampling_sees_every_ema_update_on_the_torch_adam_path(tmp_path):
+    """on the non-fused optimizer path EMA.update_model_average rebinds `.data`, which changes
+    neither the parameter version nor (reliably) its address -- the key the packed conv weights were cached under.
+    After an even number of EMA updates ema_model.sample() ran on stale packed weights.  Now the trainer / EMA mark
+    the weights as updated: the EMA model's output must equal a freshly built net holding the same state_dict."""
+    from sinddm_b200 import SinDDMNet
+    torch.manual_seed(2)
+    tr, _ = _small_trainer(tmp_path, gradient_accumulate_every=2)          # -> torch.optim.Adam + EMA class
+    tr._prepare_training()
+    assert tr._fused is None
+    dev = "cuda:0"
+    h, w = tr.model.image_sizes[1]
+    x = torch.randn(2, 3, h, w, device=dev)
+    t = torch.tensor([3, 70], device=dev)
+    with torch.no_grad():
+        tr.ema_model.denoise_fn(x, t, 1)               # packs the EMA weights once
+    for n_updates in (2, 4, 5):
+        for _ in range(n_updates):
+            tr.train_step(s=1)
+        fresh = SinDDMNet(dim=160, multiscale=True, device=dev).to(dev)
+        fresh.load_state_dict(tr.ema_model.denoise_fn.state_dict())
+        with torch.no_grad():
+            got = tr.ema_model.denoise_fn(x, t, 1)
+            want = fresh(x, t, 1)
+        assert torch.equal(got, want), f"EMA model ran on stale packed weights after {n_updates} more updates"
+    # and the EMA weights really moved
+    assert any(float((a - b).abs().max()) > 0 for a, b in zip(tr.model.parameters(), tr.ema_model.parameters()))
+
+
+def test_out_of_range_start_timestep_raises(tmp_path):
+    """custom_t >= num_timesteps indexed the schedule tables out of bounds inside the kernels; the
+    reference's gather raises for the same input."""
+    tr, _ = _small_trainer(tmp_path)
+    img = torch.zeros(1, 3, *tr.model.image_sizes[0], device="cuda:0")
+    with pytest.raises(IndexError):
+        tr.ema_model.sample_via_scale(1, img, s=1, custom_t=100)
+    with pytest.raises(IndexError):
+        tr.ema_model.sample_via_scale(1, img, s=1, custom_t=-1)
