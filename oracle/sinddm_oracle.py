@@ -309,3 +309,47 @@ def p_sample_via_scale_loop(p: Params, sch: Schedule, img, s: int, total_t: int,
         noise = torch.randn(img.shape, generator=generator)
         img = p_sample_update(sch, img, eps, t, s, noise, x_tilde)
     return img
+
+
+# ---------------------------------------------------------------------------------------------------
+# trainer step
+# ---------------------------------------------------------------------------------------------------
+
+def ema_update(ema: Params, cur: Params, beta: float) -> None:
+    """EMA.update_model_average, SinDDM/models.py:23-31: old * beta + (1 - beta) * new, parameters only (Q8)."""
+    for k in ema:
+        ema[k] = ema[k] * beta + (1 - beta) * cur[k].detach()
+
+
+def train_steps(p: Params, sch: Schedule, data_list, draws, *, lr: float, milestones: Sequence[int] = (),
+                gamma: float = 0.5, ema_decay: float = 0.995, step_start_ema: int = 2000, update_ema_every: int = 10,
+                avg_window: int = 100):
+    """MultiscaleTrainer.train, SinDDM/trainer.py:189-214, for len(draws) steps with gradient_accumulate_every=1 and
+    every random draw injected: draws[i] = (s, t, noise).  data_list[s] = (orig batch, blurry batch).
+    Returns (model params, ema params, running_loss, last lr).  Adam / MultiStepLR are torch's own, as in the
+    reference (trainer.py:134-136)."""
+    leaf = {k: v.detach().clone().requires_grad_(True) for k, v in p.items()}
+    ema = {k: v.detach().clone() for k, v in p.items()}                                                   # :100,153
+    opt = torch.optim.Adam(list(leaf.values()), lr=lr)                                                    # :134
+    sched = torch.optim.lr_scheduler.MultiStepLR(opt, milestones=list(milestones), gamma=gamma)          # :136
+    running_loss, loss_avg = [], 0.0
+    for step, (s, t, noise) in enumerate(draws):
+        x_orig, x_blur = data_list[s]
+        if int(s) > 0:                                                                                    # models.py:624-631
+            loss = p_losses(leaf, sch, x_blur, t, s, noise, x_orig=x_orig)
+        else:
+            loss = p_losses(leaf, sch, x_orig, t, s, noise)
+        loss_avg += loss.item()                                                                           # :202
+        loss.backward()
+        if step % avg_window == 0:                                                                        # :204-207 (Q5)
+            running_loss.append(loss_avg / avg_window)
+            loss_avg = 0.0
+        opt.step()                                                                                        # :208
+        opt.zero_grad()
+        if step % update_ema_every == 0:                                                                  # :211, :155-159
+            if step < step_start_ema:
+                ema = {k: v.detach().clone() for k, v in leaf.items()}
+            else:
+                ema_update(ema, leaf, ema_decay)
+        sched.step()                                                                                      # :212
+    return ({k: v.detach() for k, v in leaf.items()}, ema, running_loss, sched.get_last_lr()[0])

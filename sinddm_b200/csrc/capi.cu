@@ -79,6 +79,7 @@ int sinddm_conv_forward(const sinddm_conv_desc* d, int math, void* stream) {
     SINDDM_REQUIRE(d->in && d->w, "conv_forward: in / w are required");
     SINDDM_REQUIRE(d->out || d->out_final, "conv_forward: no output requested");
     ConvProblem p;
+    memset(&p, 0, sizeof(p));
     p.B = d->B; p.H = d->H; p.W = d->W;
     p.in = d->in; p.Cin = d->Cin; p.w = d->w; p.ntaps = d->ntaps;
     p.in_res = d->in_res; p.Cres = d->Cres; p.w_res = d->w_res; p.N = d->N;

@@ -99,6 +99,19 @@ SINDDM_DEVINL void sts_f4(uint32_t addr, float x, float y, float z, float w) {
 // ld.VOLATILE: `asm volatile` only pins the statement for the front end; to ptxas a plain ld.shared is an ordinary
 // load that it may sink towards its use or re-execute to save registers.  Tiles that the async proxy (TMA) overwrites
 // behind ptxas's back must be read exactly once, where the program says so.
+SINDDM_DEVINL float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+
+// plain shared load for tiles only this warp's generic-proxy stores write (the "memory" clobber keeps program order)
+SINDDM_DEVINL float lds_f32_plain(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+
 SINDDM_DEVINL float4 lds_f4(uint32_t addr) {
     float4 v;
     asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4];"

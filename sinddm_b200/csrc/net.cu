@@ -151,7 +151,17 @@ size_t carve(Plan* pl, uint8_t* base) {
         if (nf > partial_max) partial_max = nf;
         pl->partial = cv.take(partial_max);
         pl->dw_scratch = cv.take(dw5x5_wgrad_scratch_floats(B, pl->H, dim));
-        pl->colsum_scratch = cv.take(dw5x5_csum_scratch_floats(B, pl->H, pl->W, dim));
+        {
+            // shared by the depthwise kernels' fused column sums, colsum_launch and tc_conv's epilogue column sums
+            size_t n = dw5x5_csum_scratch_floats(B, pl->H, pl->W, dim);
+            // (tc_conv: one row per CTA and TMEM lane quarter, at most one CTA per SM; 192 >= any sm_100 part)
+            const size_t n_tc = (size_t)192 * 4 * dim, n_cs = colsum_scratch_floats(dim);
+            const size_t n_fb = final_conv_bwd_scratch_floats(half);
+            if (n_tc > n) n = n_tc;
+            if (n_cs > n) n = n_cs;
+            if (n_fb > n) n = n_fb;
+            pl->colsum_scratch = cv.take(n);
+        }
         pl->colsum_out = cv.take(dim);
         size_t doff = 0;
         for (int l = 0; l < kNumBlocks; ++l) {
@@ -338,6 +348,11 @@ int plan_build(Plan* pl, int B, int H, int W, int dim, int channels, int math, i
             b.pd2.w_blocked = b.tc_d2 && pl->blocked_weights;
             b.pd1.w_blocked = b.tc_d1 && pl->blocked_weights;
             b.pdr.w_blocked = b.tc_dr && pl->blocked_weights;
+            // dz1's column sums (= net[0]'s bias gradient) come out of the data-gradient kernel's epilogue
+            {
+                const char* e = getenv("SINDDM_TC_COLSUM");    // A/B switch; default on
+                if (b.tc_d2 && !(e && atoi(e) == 0)) b.pd2.ep.colsum_part = pl->colsum_scratch;
+            }
             if (b.tc_d2) SINDDM_TRY(tc_conv_prepare(b.pd2, &b.d2));
             if (b.tc_d1) SINDDM_TRY(tc_conv_prepare(b.pd1, &b.d1));
             if (b.tc_dr) SINDDM_TRY(tc_conv_prepare(b.pdr, &b.dr));
@@ -462,10 +477,19 @@ int net_backward(Plan* pl, const float* const* params, const float* dout_nchw, f
 
     // ---- final_conv: bias / weight gradients and the gradient into l4's output
     SINDDM_TRY(nchw_to_nhwc_launch(dout_nchw, pl->dout_nhwc, B, pl->channels, H, W, s));
-    SINDDM_TRY(colsum_launch(pl->dout_nhwc, P, pl->channels, grads[kNumParams - 1], pl->colsum_scratch, s));
-    SINDDM_TRY(simt_wgrad_launch(pl->pfw, s));
-    SINDDM_TRY(wgrad_reduce_launch(pl->partial, pl->pfw.nsplit, 1, pl->channels, pl->half, grads[kNumParams - 2], 1, s));
-    SINDDM_TRY(simt_conv_launch(pl->pfd, s));
+    const bool fused_final = pl->channels == 3 && final_conv_bwd_supported(pl->half);
+    if (fused_final) {
+        // one pass: d_o4 -> d_a, final_conv weight / bias gradients, and l4.net[2]'s (and res_conv's) bias gradient
+        const BlockBufs& b4 = pl->blk[kNumBlocks - 1];
+        SINDDM_TRY(final_conv_bwd_launch(pl->dout_nhwc, b4.o, params[kNumParams - 2], pl->d_a, P, pl->half, rnd,
+                                         grads[kNumParams - 2], grads[kNumParams - 1], grads[b4.pbase + 9],
+                                         b4.has_res ? grads[b4.pbase + 11] : nullptr, pl->colsum_scratch, s));
+    } else {
+        SINDDM_TRY(colsum_launch(pl->dout_nhwc, P, pl->channels, grads[kNumParams - 1], pl->colsum_scratch, s));
+        SINDDM_TRY(simt_wgrad_launch(pl->pfw, s));
+        SINDDM_TRY(wgrad_reduce_launch(pl->partial, pl->pfw.nsplit, 1, pl->channels, pl->half, grads[kNumParams - 2], 1, s));
+        SINDDM_TRY(simt_conv_launch(pl->pfd, s));
+    }
 
     for (int l = kNumBlocks - 1; l >= 0; --l) {
         BlockBufs& b = pl->blk[l];
@@ -474,7 +498,7 @@ int net_backward(Plan* pl, const float* const* params, const float* dout_nchw, f
 
         // bias gradients of net[2] (and res_conv, identical sum): for l < 3 they were accumulated by the depthwise
         // data-gradient launch that produced d_o (end of the previous iteration)
-        if (l == kNumBlocks - 1) {
+        if (l == kNumBlocks - 1 && !fused_final) {
             SINDDM_TRY(colsum_launch(d_o, P, b.Co, grads[b.pbase + 9], pl->colsum_scratch, s));
             if (b.has_res)
                 SINDDM_CUDA_OK(cudaMemcpyAsync(grads[b.pbase + 11], grads[b.pbase + 9], sizeof(float) * b.Co,
@@ -485,7 +509,10 @@ int net_backward(Plan* pl, const float* const* params, const float* dout_nchw, f
         if (b.has_res) SINDDM_TRY(run_wgrad(b.tc_wr, b.wgr, b.pwr, grads[b.pbase + 10], s));
         // dz1 = conv3x3^T(d_o) * gelu'(z1)
         SINDDM_TRY(run_conv(b.tc_d2, b.d2, b.pd2, s));
-        SINDDM_TRY(colsum_launch(pl->dz1, P, b.Co, grads[b.pbase + 7], pl->colsum_scratch, s));
+        if (b.tc_d2 && b.pd2.ep.colsum_part)
+            SINDDM_TRY(colsum_final_launch(pl->colsum_scratch, tc_conv_colsum_rows(b.d2), b.Co, grads[b.pbase + 7], s));
+        else
+            SINDDM_TRY(colsum_launch(pl->dz1, P, b.Co, grads[b.pbase + 7], pl->colsum_scratch, s));
         SINDDM_TRY(run_wgrad(b.tc_w0, b.wg0, b.pw0, grads[b.pbase + 6], s, b.im2col ? 2 : 0));
         // dh0 = conv3x3^T(dz1)
         SINDDM_TRY(run_conv(b.tc_d1, b.d1, b.pd1, s));

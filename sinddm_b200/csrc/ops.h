@@ -36,6 +36,9 @@ struct ConvEpilogue {
                             // dgelu_z already holds gelu'(z) (the forward epilogue has cdf and pdf at hand: two extra
                             // instructions there replace ~25 + two MUFU per value in the data-gradient epilogue)
     int fast_math;          // CUDA-core kernels: use the TF32-mode GELU (gelu_fast) instead of erff (set with math = tf32)
+    float* colsum_part;     // tensor-core path only: [grid * 4][N] per-(CTA, TMEM lane quarter) column sums of what the
+                            // kernel stores to `out` (the bias gradient of the layer below: finish with
+                            // colsum_final_launch(colsum_part, tc_conv_colsum_rows(op), N, ...)), or null
 };
 
 struct ConvProblem {
@@ -63,7 +66,13 @@ struct TcConvOp {
     int stage_bytes, nstages, smem_bytes;
     int tiles_w, tiles_h, ntiles, grid;
     int cs;   // cluster size (CTAs sharing each weight stage through TMA multicast)
+    // A/B and diagnostic switches (SINDDM_TC_*), read from the environment ONCE by tc_conv_prepare
+    int sw_peek, sw_l2pf, sw_issuers2, sw_dbg, sw_stage_release;
 };
+// rows of ConvEpilogue::colsum_part this op writes (a multiple of its grid size)
+int tc_conv_colsum_rows(const TcConvOp& op);
+// out[c] = sum over the nrows partial rows, fixed order
+int colsum_final_launch(const float* part, int nrows, int C, float* out, cudaStream_t stream);
 bool tc_conv_supported(const ConvProblem& p);
 int tc_conv_prepare(const ConvProblem& p, TcConvOp* op);
 int tc_conv_launch(const TcConvOp& op, cudaStream_t stream);
@@ -136,6 +145,15 @@ int dw5x5_launch(const float* in, const float* w /*[C][25]*/, const float* bias,
 size_t dw5x5_wgrad_scratch_floats(int B, int H, int C);
 int dw5x5_wgrad_launch(const float* x, const float* dh, float* dw, float* db, float* dcond, float* scratch, int B,
                        int H, int W, int C, cudaStream_t stream);
+
+// final_conv (1x1, C -> 3) backward in one pass: d_o = W^T dout (tf32-rounded when round), dw [3][C], db [3], and
+// db_prev [C] (+ optional copy db_prev2) = column sums of the UNROUNDED d_o = W^T db.  dout_nhwc3 [P,3], o / d_o [P,C],
+// w [3][C].  scratch: final_conv_bwd_scratch_floats(C) floats.
+size_t final_conv_bwd_scratch_floats(int C);
+bool final_conv_bwd_supported(int C);
+int final_conv_bwd_launch(const float* dout_nhwc3, const float* o, const float* w, float* d_o, long long P, int C,
+                          int round, float* dw, float* db, float* db_prev, float* db_prev2, float* scratch,
+                          cudaStream_t stream);
 
 // out[c] = sum_p a[p][c]; scratch needs colsum_scratch_floats(C) floats.
 size_t colsum_scratch_floats(int C);

@@ -72,6 +72,111 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, float* __rest
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// final_conv backward (reference SinDDM/models.py:130-132,151: 1x1 conv C -> 3) in ONE pass over the C-channel tensors:
+//     d_o[p][c]  = sum_j W[j][c] * dout[p][j]            (gradient into the last block's output; tf32-rounded on request)
+//     dW[j][c]   = sum_p dout[p][j] * o[p][c]            (per-block partial sums, fixed-order finish below)
+//     db[j]      = sum_p dout[p][j]
+// reads o (C channels) once and writes d_o once: 2 * P * C * 4 bytes, HBM bound.  Replaces five launches (3-channel
+// column sum, CUDA-core weight gradient + reduce, CUDA-core data gradient) that read / wrote the same bytes 2.3 times,
+// and the column sum of d_o (the last block's bias gradient), which is W^T db exactly -- no pass over memory at all.
+// A thread owns 4 consecutive channels (one 16-byte access) of every (blockDim.x / (C/4))-th pixel of its block's range.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kFinalBwdBlocks = 592;   // 4 per SM
+constexpr int kFinalBwdThreads = 240;
+
+__global__ void __launch_bounds__(kFinalBwdThreads)
+final_conv_bwd_kernel(const float* __restrict__ dout3, const float* __restrict__ o, const float* __restrict__ w,
+                      float* __restrict__ d_o, long long P, int C, int round, float* __restrict__ part) {
+    extern __shared__ float red[];   // [groups][16]
+    const int c4n = C >> 2;                                   // threads per pixel
+    const int groups = blockDim.x / c4n;
+    const int g = threadIdx.x / c4n, c4 = threadIdx.x - g * c4n;
+    const bool active = g < groups;
+    const long long p_begin = P * blockIdx.x / gridDim.x, p_end = P * (blockIdx.x + 1) / gridDim.x;
+    float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0, w2 = w0;
+    if (active) {
+        // scalar loads: parameters are views into a flat buffer, aligned to 4 bytes only
+        const float* wp = w + 4 * c4;
+        w0 = make_float4(__ldg(wp), __ldg(wp + 1), __ldg(wp + 2), __ldg(wp + 3));
+        w1 = make_float4(__ldg(wp + C), __ldg(wp + C + 1), __ldg(wp + C + 2), __ldg(wp + C + 3));
+        w2 = make_float4(__ldg(wp + 2 * C), __ldg(wp + 2 * C + 1), __ldg(wp + 2 * C + 2), __ldg(wp + 2 * C + 3));
+    }
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0;
+    float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+    if (active) {
+#pragma unroll 2
+        for (long long q = p_begin + g; q < p_end; q += groups) {
+            const float d0 = __ldg(dout3 + q * 3 + 0), d1 = __ldg(dout3 + q * 3 + 1), d2 = __ldg(dout3 + q * 3 + 2);
+            const float4 x = __ldg(reinterpret_cast<const float4*>(o + q * C) + c4);
+            a0.x = fmaf(d0, x.x, a0.x); a0.y = fmaf(d0, x.y, a0.y); a0.z = fmaf(d0, x.z, a0.z); a0.w = fmaf(d0, x.w, a0.w);
+            a1.x = fmaf(d1, x.x, a1.x); a1.y = fmaf(d1, x.y, a1.y); a1.z = fmaf(d1, x.z, a1.z); a1.w = fmaf(d1, x.w, a1.w);
+            a2.x = fmaf(d2, x.x, a2.x); a2.y = fmaf(d2, x.y, a2.y); a2.z = fmaf(d2, x.z, a2.z); a2.w = fmaf(d2, x.w, a2.w);
+            b0 += d0; b1 += d1; b2 += d2;
+            float4 y;
+            y.x = fmaf(w2.x, d2, fmaf(w1.x, d1, w0.x * d0));
+            y.y = fmaf(w2.y, d2, fmaf(w1.y, d1, w0.y * d0));
+            y.z = fmaf(w2.z, d2, fmaf(w1.z, d1, w0.z * d0));
+            y.w = fmaf(w2.w, d2, fmaf(w1.w, d1, w0.w * d0));
+            if (round) { y.x = round_tf32(y.x); y.y = round_tf32(y.y); y.z = round_tf32(y.z); y.w = round_tf32(y.w); }
+            reinterpret_cast<float4*>(d_o + q * C)[c4] = y;
+        }
+    }
+    // block partials in a fixed order: for each of the 12 sums of this thread's channel quad, add the pixel groups 0..G-1
+    float* mine = red + (size_t)threadIdx.x * 16;
+    mine[0] = a0.x; mine[1] = a0.y; mine[2] = a0.z; mine[3] = a0.w;
+    mine[4] = a1.x; mine[5] = a1.y; mine[6] = a1.z; mine[7] = a1.w;
+    mine[8] = a2.x; mine[9] = a2.y; mine[10] = a2.z; mine[11] = a2.w;
+    mine[12] = b0; mine[13] = b1; mine[14] = b2; mine[15] = 0.f;
+    __syncthreads();
+    // part[block][3*C + 3]: dW partial rows j = 0..2 then the 3 db partials
+    float* dst = part + (size_t)blockIdx.x * (3 * C + 4);
+    for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) {
+        const int j = i / C, c = i - j * C;
+        float s = 0.f;
+        for (int gg = 0; gg < groups; ++gg) s += red[(size_t)(gg * c4n + (c >> 2)) * 16 + j * 4 + (c & 3)];
+        dst[i] = s;
+    }
+    if (threadIdx.x < 3) {
+        float s = 0.f;
+        for (int gg = 0; gg < groups; ++gg) s += red[(size_t)(gg * c4n) * 16 + 12 + threadIdx.x];
+        dst[3 * C + threadIdx.x] = s;
+    }
+}
+
+// dW[j][c], db[j] = fixed-order sums of the block partials; db_prev[c] = sum_j W[j][c] * db[j].  One warp per output
+// value (lanes stride over the partial rows, fixed shuffle tree); every block recomputes the three db sums it needs.
+__global__ void __launch_bounds__(256)
+final_conv_bwd_finish_kernel(const float* __restrict__ part, int nblk, int C, const float* __restrict__ w,
+                             float* __restrict__ dw, float* __restrict__ db, float* __restrict__ db_prev,
+                             float* __restrict__ db_prev2) {
+    __shared__ float sdb[3];
+    const int stride = 3 * C + 4;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    auto column = [&](int i) {
+        float s = 0.f;
+        for (int k = lane; k < nblk; k += 32) s += part[(size_t)k * stride + i];
+        return warp_sum(s);
+    };
+    if (warp < 3) {
+        const float s = column(3 * C + warp);
+        if (lane == 0) {
+            sdb[warp] = s;
+            if (blockIdx.x == 0) db[warp] = s;
+        }
+    }
+    for (int i = blockIdx.x * nwarps + warp; i < 3 * C; i += gridDim.x * nwarps) {
+        const float s = column(i);
+        if (lane == 0) dw[i] = s;
+    }
+    __syncthreads();
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
+        const float v = fmaf(w[2 * C + c], sdb[2], fmaf(w[C + c], sdb[1], w[c] * sdb[0]));
+        db_prev[c] = v;
+        if (db_prev2) db_prev2[c] = v;
+    }
+}
+
 inline int grid_for(long long total, int block) {
     long long g = (total + block - 1) / block;
     const long long cap = 148ll * 16;
@@ -94,6 +199,32 @@ int colsum_launch(const float* a, long long P, int C, float* out, float* scratch
     colsum_partial_kernel<<<nblk, block, (size_t)lanes * C * sizeof(float), stream>>>(a, P, C, scratch);
     SINDDM_CUDA_OK(cudaGetLastError());
     colsum_final_kernel<<<ceil_div(C, 32), dim3(32, 8), 0, stream>>>(scratch, nblk, C, out);
+    SINDDM_CUDA_OK(cudaGetLastError());
+    return SINDDM_OK;
+}
+
+size_t final_conv_bwd_scratch_floats(int C) { return (size_t)kFinalBwdBlocks * (3 * C + 4); }
+
+bool final_conv_bwd_supported(int C) { return C % 4 == 0 && C >= 4 && C / 4 <= kFinalBwdThreads; }
+
+int final_conv_bwd_launch(const float* dout_nhwc3, const float* o, const float* w, float* d_o, long long P, int C,
+                          int round, float* dw, float* db, float* db_prev, float* db_prev2, float* scratch,
+                          cudaStream_t stream) {
+    SINDDM_REQUIRE(final_conv_bwd_supported(C), "final_conv_bwd: C=%d unsupported", C);
+    const int c4n = C / 4;
+    const int threads = (kFinalBwdThreads / c4n) * c4n;
+    int nblk = kFinalBwdBlocks;
+    if ((long long)nblk > P) nblk = (int)P;
+    final_conv_bwd_kernel<<<nblk, threads, (size_t)threads * 16 * sizeof(float), stream>>>(dout_nhwc3, o, w, d_o, P, C,
+                                                                                         round, scratch);
+    SINDDM_CUDA_OK(cudaGetLastError());
+    final_conv_bwd_finish_kernel<<<16, 256, 0, stream>>>(scratch, nblk, C, w, dw, db, db_prev, db_prev2);
+    SINDDM_CUDA_OK(cudaGetLastError());
+    return SINDDM_OK;
+}
+
+int colsum_final_launch(const float* part, int nrows, int C, float* out, cudaStream_t stream) {
+    colsum_final_kernel<<<ceil_div(C, 32), dim3(32, 8), 0, stream>>>(part, nrows, C, out);
     SINDDM_CUDA_OK(cudaGetLastError());
     return SINDDM_OK;
 }

@@ -82,6 +82,10 @@ struct KernelArgs {
     uint32_t idesc;
     int issuers2;              // single-CTA kernel: warps 1 and 2 each issue the MMAs of one half tile (SINDDM_TC_ISSUERS=1: warp 1 issues both)
     int peek;                  // MMA warps test the next weight box's barrier inside the MMA asm, no per-box tcgen05 fence (SINDDM_TC_PEEK=0: off)
+    int stage_release;         // narrow layers (weight ring >= 2 2/3 stages): the MMA warps commit ONE barrier per stage (the
+                               // halo box's empty barrier) that also releases the stage's weight boxes, instead of
+                               // one commit per box -- every tcgen05.commit costs its warp ~230 cycles, as long as the
+                               // four N = 80 MMAs of a box execute (SINDDM_TC_STAGE_RELEASE=0: off)
     int l2pf;                  // warp 3 prefetches the streamed epilogue operand into L2 one tile ahead (SINDDM_TC_L2PF=1)
     int dbg;                   // diagnostics (SINDDM_TC_DEBUG): 1 = no operand loads, 2 = no epilogue traffic, 4 = no MMAs, 8 = stage but do not store
     ConvEpilogue ep;
@@ -191,6 +195,21 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         // ------------------------------------------------------------ TMA producer
         int sa_i = 0, sb_i = 0;
         uint32_t pha = 0, phb = 0;
+        // stage_release bookkeeping: stages are released in order through the halo boxes' empty barriers; `rel` stages
+        // (holding `rel_boxes` weight boxes) are known to be released; jst / kbox count the stages / boxes loaded so far
+        const bool srel = !TWO && a.stage_release;
+        int rel = 0, rel_boxes = 0, rel_local = 0, rel_slot = 0, jst = 0, kbox = 0;
+        uint32_t rel_par = 0;
+        auto release_one = [&]() {
+            mbar_wait(&emptya_bar[rel_slot], rel_par);
+            rel_boxes += (rel_local < nst_main) ? nky : 1;
+            if (++rel_local == nst) rel_local = 0;
+            if (++rel_slot == kStagesA) {
+                rel_slot = 0;
+                rel_par ^= 1u;
+            }
+            ++rel;
+        };
         for (int st = pair_id; st < nsuper; st += npairs) {
             // a tile index past the end (odd tile count, second CTA of the last pair) runs the same pipeline on
             // zeros: image index >= B is out of bounds for TMA, which zero-fills the box
@@ -204,7 +223,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                 const int c = main ? it / nkx : it - nst_main;
                 const int kx = main ? it - c * nkx : 0;
                 // activation halo box: rows h0-1 .. h0+16, columns shifted by the horizontal tap
-                mbar_wait(&emptya_bar[sa_i], pha ^ 1u);
+                if (srel) {
+                    while (rel < jst - kStagesA + 1) release_one();
+                    ++jst;
+                } else {
+                    mbar_wait(&emptya_bar[sa_i], pha ^ 1u);
+                }
                 if (!TWO && (a.dbg & 1)) {
                     mbar_arrive_expect_tx_w(&fulla_bar[sa_i], 0);
                 } else if (!TWO) {
@@ -226,7 +250,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                 const int kys = main ? nky : 1;
                 for (int ky = 0; ky < kys; ++ky) {
                     const int tap = (main && nkx == 3) ? ky * 3 + kx : 0;
-                    mbar_wait(&emptyb_bar[sb_i], phb ^ 1u);
+                    if (srel) {
+                        // slot kbox % nstages_b was last used by box kbox - nstages_b: its whole stage must be done
+                        while (rel_boxes < kbox - a.nstages_b + 1) release_one();
+                        ++kbox;
+                    } else {
+                        mbar_wait(&emptyb_bar[sb_i], phb ^ 1u);
+                    }
                     if (!TWO && (a.dbg & 1)) {
                         mbar_arrive_expect_tx_w(&fullb_bar[sb_i], 0);
                     } else if (!TWO) {
@@ -307,11 +337,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                     if (a.peek && !(a.dbg & 4)) {
                         const uint32_t r = umma_tf32_ss_x4_test(dacc, ad, bd, desc_hi, 2u, a.idesc, (it | ky) != 0 ? 1u : 0u,
                                                                 nmma, &fullb_bar[sb_i], phb);
-                        umma_commit_elect(&emptyb_bar[sb_cur]);
+                        if (!a.stage_release) umma_commit_elect(&emptyb_bar[sb_cur]);
                         b_ready = __all_sync(0xffffffffu, r != 0);
                     } else {
                         if (!(a.dbg & 4)) umma_tf32_ss_x4(dacc, ad, bd, desc_hi, 2u, a.idesc, (it | ky) != 0 ? 1u : 0u, nmma);
-                        umma_commit_elect(&emptyb_bar[sb_cur]);
+                        if (!a.stage_release) umma_commit_elect(&emptyb_bar[sb_cur]);
                         b_ready = false;
                     }
                 }
@@ -475,6 +505,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         const float* gsrc2 = (ep.res_add && ep.dgelu_z) ? ep.dgelu_z : nullptr;   // rare second stream: plain loads
         uint32_t slot_uses[kSlots] = {0, 0, 0};
         int titer = 0;
+        // ep.colsum_part: column sums of everything this warp stores to `out` (its column share, its pixel quarter),
+        // kept in lanes 0-15 (one column each) per chunk of the warp, written once at the end of the kernel
+        float csum_acc[kMaxN / (2 * kEpiChunk)];
+#pragma unroll
+        for (int i = 0; i < kMaxN / (2 * kEpiChunk); ++i) csum_acc[i] = 0.f;
         for (int st = pair_id; st < nsuper; st += npairs, ++titer) {
             const int tile = st * CS + crank;
             const int tw = tile % a.tiles_w;
@@ -488,6 +523,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                 const int hq = th * kTileH + half * 8 + quarter * 2, w0 = tw * kTileW;   // this warp's strip
                 const bool valid = live && (h < a.H) && (w < a.W);
                 const size_t pix = ((size_t)b * a.H + h) * a.W + w;
+                const unsigned vmask = ep.colsum_part ? __ballot_sync(0xffffffffu, valid) : 0u;
 
                 float x3v[3] = {0.f, 0.f, 0.f};
                 if (ep.x3 && valid) {
@@ -509,7 +545,39 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                 tc_fence_after_sync();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(slot * a.slot_stride);
 
-                auto store_tile = [&](const CUtensorMap* map, const int cc, const float (&v)[16]) {
+                // column sums of a staged [32 px][16 ch] tile: lanes 0-15 walk the even rows of "their" column, lanes 16-31
+                // the odd rows (one 128-byte wavefront per step: conflict free under the 64B swizzle); pixels outside
+                // the image are skipped.  0.08 instructions per value, against 5 for a shuffle reduction of registers.
+                auto tile_colsum = [&](const uint32_t tile_u32, float& acc) {
+                    // row r = 2i + odd: (r >> 1) & 3 = i & 3 for both parities, so the swizzled column offset only depends
+                    // on i & 3 -> four lane-dependent base addresses, every load is base + immediate
+                    const uint32_t j = (uint32_t)lane & 15u, odd = (uint32_t)lane >> 4;
+                    const uint32_t base = tile_u32 + odd * 64u + ((j & 3u) << 2);
+                    const uint32_t q = j >> 2;
+                    const uint32_t b0 = base + ((q ^ 0u) << 4), b1 = base + ((q ^ 1u) << 4), b2 = base + ((q ^ 2u) << 4),
+                                   b3 = base + ((q ^ 3u) << 4);
+                    float x[16];
+#pragma unroll
+                    for (uint32_t i = 0; i < 16; i += 4) {
+                        x[i + 0] = lds_f32_plain(b0 + (i + 0) * 128u);
+                        x[i + 1] = lds_f32_plain(b1 + (i + 1) * 128u);
+                        x[i + 2] = lds_f32_plain(b2 + (i + 2) * 128u);
+                        x[i + 3] = lds_f32_plain(b3 + (i + 3) * 128u);
+                    }
+                    if (vmask != 0xffffffffu) {
+#pragma unroll
+                        for (uint32_t i = 0; i < 16; ++i)
+                            if (!((vmask >> (2u * i + odd)) & 1u)) x[i] = 0.f;
+                    }
+                    // fixed association: four independent chains of four, then a tree
+                    const float s0 = (x[0] + x[4]) + (x[8] + x[12]), s1 = (x[1] + x[5]) + (x[9] + x[13]);
+                    const float s2 = (x[2] + x[6]) + (x[10] + x[14]), s3 = (x[3] + x[7]) + (x[11] + x[15]);
+                    float s = (s0 + s1) + (s2 + s3);
+                    s += __shfl_xor_sync(0xffffffffu, s, 16);
+                    acc += s;
+                };
+
+                auto store_tile = [&](const CUtensorMap* map, const int cc, const float (&v)[16], float* csum = nullptr) {
                     // with a streamed operand tile 1 is the only store buffer, otherwise the two tiles alternate
                     uint8_t* buf = stg_in + (gsrc ? 1 : obuf) * kEpiTileBytes;
                     obuf ^= 1;
@@ -529,10 +597,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                         tma_store_4d(map, buf, cc, w0, hq, b);
                         bulk_commit_group();
                     }
+                    if (csum) tile_colsum(stg_u32 + bo, *csum);   // the tile stays intact until its next wait_group_read
                 };
 
                 // TMEM -> register loads are double buffered: chunk i+1 is in flight while chunk i is processed
-                auto process = [&](const int cc, const uint32_t (&raw)[16]) {
+                auto process = [&](const int cc, const uint32_t (&raw)[16], float& csum) {
                     float v[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
@@ -654,7 +723,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 #pragma unroll
                             for (int j = 0; j < 16; ++j) v[j] = round_tf32(v[j]);
                         }
-                        store_tile(&tm_out, cc, v);
+                        store_tile(&tm_out, cc, v, ep.colsum_part ? &csum : nullptr);
                     }
                 };
                 {
@@ -676,7 +745,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                     }
 #pragma unroll
                     for (int i = 0; i < kMaxN / (2 * kEpiChunk); ++i)
-                        if (cc + i * 2 * kEpiChunk < N) process(cc + i * 2 * kEpiChunk, r[i]);
+                        if (cc + i * 2 * kEpiChunk < N) process(cc + i * 2 * kEpiChunk, r[i], csum_acc[i]);
                 }
 
                 if (ep.w_final) {
@@ -700,6 +769,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         }
         if (lane == 0) bulk_wait_group_read<0>();   // the staging tiles are read until the last store has drained
         __syncwarp();
+        if (ep.colsum_part && lane < 16) {
+            float* dst = ep.colsum_part + ((size_t)blockIdx.x * 4 + quarter) * N + cgrp * kEpiChunk + lane;
+#pragma unroll
+            for (int i = 0; i < kMaxN / (2 * kEpiChunk); ++i)
+                if (cgrp * kEpiChunk + i * 2 * kEpiChunk < N) dst[i * 2 * kEpiChunk] = csum_acc[i];
+        }
     }
 
     // ---------------------------------------------------------------- teardown
@@ -723,6 +798,8 @@ static int two_sm_setting() {
     }
     return v;
 }
+
+int tc_conv_colsum_rows(const TcConvOp& op) { return op.grid * 4; }
 
 bool tc_conv_supported(const ConvProblem& p) {
     if (p.Cin < 8 || p.Cin % 8 != 0) return false;
@@ -784,18 +861,31 @@ int tc_conv_prepare(const ConvProblem& p, TcConvOp* op) {
     int npairs = device_info().num_sms / cs;
     if (npairs > nsuper) npairs = nsuper;
     op->grid = npairs * cs;
+    // switches: read here (plan build / single-operator call), never per launch
+    auto env_int = [](const char* name, int dflt) {
+        const char* e = getenv(name);
+        return e ? atoi(e) : dflt;
+    };
+    op->sw_peek = env_int("SINDDM_TC_PEEK", 1) != 0;
+    op->sw_l2pf = env_int("SINDDM_TC_L2PF", 0) != 0;            // measured neutral (profiles/): off unless asked for
+    op->sw_issuers2 = env_int("SINDDM_TC_ISSUERS", 2) != 1;
+    op->sw_dbg = env_int("SINDDM_TC_DEBUG", 0);                 // diagnostic runs only: results are wrong when set
+    // stage-granular release needs the ring to hold two whole stages plus the boxes in flight behind them
+    const int nky = p.ntaps == 9 ? 3 : 1;
+    op->sw_stage_release = env_int("SINDDM_TC_STAGE_RELEASE", 1) != 0 && cs == 1 && op->sw_issuers2 && nst >= 2 * nky + 2;
     return SINDDM_OK;
 }
 
 int tc_conv_launch(const TcConvOp& op, cudaStream_t stream) {
-    static int smem_set = 0;
-    if (!smem_set) {
-        SINDDM_CUDA_OK(cudaFuncSetAttribute(tc_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            device_info().max_smem_optin));
-        SINDDM_CUDA_OK(cudaFuncSetAttribute(tc_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            device_info().max_smem_optin));
-        smem_set = 1;
-    }
+    // opt-in shared memory size: set once per process (function-local static: thread-safe initialisation)
+    static const cudaError_t smem_set = []() {
+        cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             device_info().max_smem_optin);
+        if (e != cudaSuccess) return e;
+        return cudaFuncSetAttribute(tc_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    device_info().max_smem_optin);
+    }();
+    SINDDM_CUDA_OK(smem_set);
     const ConvProblem& p = op.p;
     KernelArgs a;
     a.B = p.B;
@@ -816,22 +906,11 @@ int tc_conv_launch(const TcConvOp& op, cudaStream_t stream) {
     a.idesc = umma_idesc_tf32(op.cs == 2 ? 256 : 128, p.N, 0, 0);
     a.w_blk = p.w_blocked ? p.w : nullptr;
     a.wres_blk = p.w_blocked ? p.w_res : nullptr;
-    {
-        const char* e = getenv("SINDDM_TC_PEEK");
-        a.peek = e ? (atoi(e) != 0) : 1;
-    }
-    {
-        const char* e = getenv("SINDDM_TC_L2PF");    // measured neutral (profiles/): off unless asked for
-        a.l2pf = e ? (atoi(e) != 0) : 0;
-    }
-    {
-        const char* e = getenv("SINDDM_TC_ISSUERS");
-        a.issuers2 = e ? (atoi(e) != 1) : 1;
-    }
-    {
-        const char* e = getenv("SINDDM_TC_DEBUG");   // diagnostic runs only: results are wrong when set
-        a.dbg = e ? atoi(e) : 0;
-    }
+    a.peek = op.sw_peek;
+    a.l2pf = op.sw_l2pf;
+    a.issuers2 = op.sw_issuers2;
+    a.dbg = op.sw_dbg;
+    a.stage_release = op.sw_stage_release;
     a.ep = p.ep;
     // algorithmic work: real pixels x N x (taps*Cin + Cres) MACs
     prof_begin(stream, 0, 2.0 * (double)p.B * p.H * p.W * p.N * ((double)p.ntaps * p.Cin + a.Cres));

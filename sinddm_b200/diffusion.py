@@ -286,7 +286,7 @@ class MultiScaleGaussianDiffusion(nn.Module):
         x = x.contiguous()
         eps = self.denoise_fn(x, t, scale=s)
         # drawn every step, also when unused (Q7)
-        noise = noise_like(x.shape, x.device, repeat_noise) if self.dp_world == 1 else self._randn(x.shape, x.device)
+        noise = noise_like(x.shape, x.device, True) if repeat_noise else self._randn(x.shape, x.device)
         reblur = bool(self.reblurring) and s > 0
         return ops.ddpm_step(x, eps, noise, t, self._tables(),
                              x_tilde=self.img_prev_upsample.contiguous() if reblur else None,

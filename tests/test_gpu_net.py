@@ -84,8 +84,8 @@ def test_train_loss_and_grads_vs_reference_golden(golden, math):
 
 @pytest.mark.parametrize("math", ["fp32", "tf32"])
 def test_p_sample_vs_reference_golden(golden, math):
-    """The reference draws the step noise with torch.randn on ITS device (CPU there); here it is injected by
-    monkeypatching noise_like so the fused ddpm_step sees the golden draw."""
+    """The reference draws the step noise with torch.randn on ITS device (CPU there); here it is injected through
+    the diffusion object's single noise entry point (_randn) so the fused ddpm_step sees the golden draw."""
     import sinddm_b200.diffusion as D
     g = golden("g4_p_sample.npz")
     net, dif = build(math)
@@ -97,6 +97,7 @@ def test_p_sample_vs_reference_golden(golden, math):
             dif.img_prev_upsample = rs_tensor(400 + 10 * s + ti, (2, 3, h, w), 0.5).clamp(-1, 1).to(DEV)
             noise = torch.from_numpy(g[f"s{s}_t{ti}_noise"]).to(DEV)
             D.noise_like = lambda shape, device, repeat=False: noise
+            dif._randn = lambda shape, device, noise=noise: noise
             out = dif.p_sample(xt, torch.full((2,), ti, device=DEV, dtype=torch.long), s)
             tol_check(out, g[f"s{s}_t{ti}_out"], math, f"s={s} t={ti}")
     finally:

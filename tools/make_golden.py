@@ -192,8 +192,197 @@ def main():
         g6[k + "/wsum"] = np.array(int((a.astype(np.int64).reshape(-1) * (np.arange(a.size) % 251)).sum()))
     np.savez_compressed(OUT / "g6_pyramid.npz", **g6)
 
+    make_r02_goldens(orc, net, params)
     for f in sorted(OUT.glob("*.npz")):
         print(f.name, f.stat().st_size)
+
+
+def _store_grads(dst, prefix, named_params):
+    """Small tensors whole; big ones as their L2 norm plus a fixed strided sample (as G2 does)."""
+    for name, prm in named_params:
+        g = prm.grad.detach().numpy() if prm.grad is not None else prm.detach().numpy()
+        if g.size <= 4096:
+            dst[f"{prefix}/{name}"] = g
+        else:
+            dst[f"{prefix}_norm/{name}"] = np.array(np.linalg.norm(g.astype(np.float64)))
+            dst[f"{prefix}_sample/{name}"] = g.reshape(-1)[:: max(1, g.size // 512)][:512]
+
+
+def make_r02_goldens(orc, net, params):
+    """Round-2 fixtures: parity where the metric lives.
+    G7  reference forward + loss + all 52 gradients at the BASELINE finest scale (186x248, B=2, s=4);
+    G8  the authors' trained forest EMA weights (committed as a fixture) on the real noisy forest image at
+        t in {2, 50, 95}, scales 0 and 3, plus the SURVEY 8c anchor input;
+    G9  four steps of the reference MultiscaleTrainer.train() with every drawn (s, t, noise) recorded."""
+    from PIL import Image
+    from SinDDM.functions import create_img_scales
+    from SinDDM.models import MultiScaleGaussianDiffusion, SinDDMNet
+    from SinDDM.trainer import MultiscaleTrainer
+
+    # ---- G7 --------------------------------------------------------------------------------------------------
+    bal_sizes = [(64, 48), (90, 67), (126, 94), (177, 133), (248, 186)]
+    bal_losses = [1.20, 0.85, 0.60, 0.42]
+    dif = MultiScaleGaussianDiffusion(denoise_fn=net, n_scales=5, scale_factor=1.403, image_sizes=bal_sizes,
+                                      timesteps=100, train_full_t=True, scale_losses=bal_losses, loss_type="l1",
+                                      reblurring=True, omega=0, device="cpu", results_folder=tempfile.mkdtemp())
+    g7 = {}
+    s = 4
+    h, w = bal_sizes[s][1], bal_sizes[s][0]
+    x_orig = rs_tensor(700, (2, 3, h, w), 0.5).clamp(-1, 1)
+    x_blur = rs_tensor(701, (2, 3, h, w), 0.5).clamp(-1, 1)
+    net.zero_grad()
+    torch.manual_seed(4321)
+    loss = dif((x_orig, x_blur), s)
+    loss.backward()
+    torch.manual_seed(4321)
+    t_drawn = torch.randint(0, dif.num_timesteps_trained[s], (2,)).long()
+    noise_drawn = torch.randn_like(x_orig)
+    with torch.no_grad():
+        x_noisy = dif.q_sample(x_start=dif.gammas[s - 1][t_drawn].reshape(-1, 1, 1, 1) * x_blur +
+                               (1 - dif.gammas[s - 1][t_drawn].reshape(-1, 1, 1, 1)) * x_orig, t=t_drawn,
+                               noise=noise_drawn)
+        pred = net(x_noisy, t_drawn, scale=s)
+    assert abs(float((noise_drawn - pred).abs().mean()) - float(loss)) < 1e-6, "G7 replay does not match forward()"
+    g7["t"] = t_drawn.numpy()
+    g7["noise_seed_check"] = noise_drawn.reshape(-1)[::9973].numpy()      # noise itself: replayed by the test from the
+    g7["noise"] = noise_drawn.numpy().astype(np.float16)                   # float16 copy is NOT used for parity; see below
+    g7["loss"] = loss.detach().numpy()
+    pn = pred.numpy()
+    g7["pred_norm"] = np.array(np.linalg.norm(pn.astype(np.float64)))
+    g7["pred_sample"] = pn.reshape(-1)[::53][:8192]
+    g7["pred_corner"] = pn[:, :, :4, :4]
+    g7["pred_border_row"] = pn[:, :, -1, :]
+    _store_grads(g7, "grad", net.named_parameters())
+    del g7["noise"]
+    np.savez_compressed(OUT / "g7_finest_scale.npz", **g7)
+    # the drawn noise is 2x3x186x248 fp32 = 1.1 MB: stored losslessly in its own file
+    np.savez_compressed(OUT / "g7_noise.npz", noise=noise_drawn.numpy())
+
+    # ---- G8 --------------------------------------------------------------------------------------------------
+    ck = torch.load(str(REF / "results" / "forest" / "model-12.pt"), map_location="cpu", weights_only=False)
+    ema_sd = ck["ema"]
+    np.savez_compressed(OUT / "forest_ema_state.npz", **{k: v.numpy() for k, v in ema_sd.items()})
+    g8 = {}
+    with tempfile.TemporaryDirectory() as td:
+        import shutil
+        shutil.copy(str(REF / "datasets" / "forest" / "forest.png"), os.path.join(td, "forest.png"))
+        szs, losses, sf, ns = create_img_scales(td + "/", "forest.png", scale_factor=1.411, create=True, auto_scale=50000)
+        fnet = SinDDMNet(dim=160, multiscale=True, device="cpu")
+        fdif = MultiScaleGaussianDiffusion(denoise_fn=fnet, n_scales=ns, scale_factor=sf, image_sizes=szs,
+                                           timesteps=100, train_full_t=True, scale_losses=losses, loss_type="l1",
+                                           reblurring=True, omega=0, device="cpu", results_folder=tempfile.mkdtemp())
+        print("forest load_state_dict:", fdif.load_state_dict(ema_sd, strict=True))
+        g8["sizes"] = np.array(szs)
+        g8["n_scales"] = np.array(ns)
+        from torchvision import transforms
+        to_t = transforms.Compose([transforms.ToTensor(), transforms.Lambda(lambda t: (t * 2) - 1)])
+        for sc in (0, 3):
+            img_u8 = np.asarray(Image.open(os.path.join(td, f"scale_{sc}", "forest.png")).convert("RGB"))
+            g8[f"s{sc}_img_u8"] = img_u8
+            x0 = to_t(Image.fromarray(img_u8)).unsqueeze(0)
+            if sc > 0:
+                rec_u8 = np.asarray(Image.open(os.path.join(td, f"scale_{sc}_recon", "forest.png")).convert("RGB"))
+                g8[f"s{sc}_recon_u8"] = rec_u8
+                xb = to_t(Image.fromarray(rec_u8)).unsqueeze(0)
+            for ti in (2, 50, 95):
+                tt = torch.tensor([ti], dtype=torch.long)
+                noise = rs_tensor(800 + 10 * sc + ti, x0.shape)
+                with torch.no_grad():
+                    if sc > 0:
+                        gam = fdif.gammas[sc - 1][tt].reshape(-1, 1, 1, 1)
+                        xin = fdif.q_sample(x_start=gam * xb + (1 - gam) * x0, t=tt, noise=noise)
+                        lossv = fdif.p_losses(xb, tt, sc, noise=noise, x_orig=x0)
+                    else:
+                        xin = fdif.q_sample(x_start=x0, t=tt, noise=noise)
+                        lossv = fdif.p_losses(x0, tt, sc, noise=noise)
+                    eps = fnet(xin, tt, scale=sc)
+                assert abs(float((noise - eps).abs().mean()) - float(lossv)) < 1e-6
+                g8[f"s{sc}_t{ti}_eps"] = eps.numpy()
+                g8[f"s{sc}_t{ti}_loss"] = lossv.numpy()
+        # SURVEY.md 8c anchor input
+        gen = torch.Generator().manual_seed(1234)
+        xa = torch.randn(2, 3, 42, 75, generator=gen)
+        ta = torch.tensor([7, 93], dtype=torch.long)
+        with torch.no_grad():
+            for sc in (0, 3):
+                ya = fnet(xa, ta, scale=sc)
+                g8[f"anchor_s{sc}"] = ya.numpy()
+                print(f"anchor scale={sc}: mean {float(ya.mean()):.6f} std {float(ya.std()):.6f} y[0,0,0,:4] {ya[0, 0, 0, :4].tolist()}")
+        g8["anchor_x"] = xa.numpy()
+    np.savez_compressed(OUT / "g8_forest_weights.npz", **g8)
+
+    # ---- G9 --------------------------------------------------------------------------------------------------
+    g9 = {}
+    with tempfile.TemporaryDirectory() as td:
+        img = synthetic_image(21, 124, 93)
+        Image.fromarray(img).save(os.path.join(td, "synth.png"))
+        szs, losses, sf, ns = create_img_scales(td + "/", "synth.png", scale_factor=1.411, create=True, auto_scale=50000)
+        tnet = SinDDMNet(dim=160, multiscale=True, device="cpu")
+        tnet.load_state_dict(params, strict=True)
+        tdif = MultiScaleGaussianDiffusion(denoise_fn=tnet, n_scales=ns, scale_factor=sf, image_sizes=szs, timesteps=100,
+                                           train_full_t=True, scale_losses=losses, loss_type="l1", reblurring=True,
+                                           omega=0, device="cpu", results_folder=os.path.join(td, "res"))
+        torch.manual_seed(99)
+        tr = MultiscaleTrainer(tdif, td + "/", n_scales=ns, scale_factor=sf, image_sizes=szs, train_batch_size=2,
+                               train_lr=1e-3, train_num_steps=4, gradient_accumulate_every=1, ema_decay=0.995,
+                               fp16=False, step_start_ema=2, update_ema_every=1, save_and_sample_every=10 ** 9,
+                               avg_window=2, sched_milestones=[3], results_folder=os.path.join(td, "res"), device="cpu")
+        g9["sizes"] = np.array(szs)
+        g9["scale_losses"] = np.array(losses, dtype=np.float64)
+        g9["scale_factor"] = np.array(sf)
+        g9["n_scales"] = np.array(ns)
+        for i in range(ns):
+            # data_list rows are identical images: keep row 0 as uint8 (exactly recoverable: ToTensor()*2-1 of uint8)
+            for j, name in enumerate(("orig", "blur")):
+                u8 = ((tr.data_list[i][j][0] + 1) * 0.5 * 255).round().to(torch.uint8).numpy()
+                assert torch.equal((torch.from_numpy(u8).float().div(255) * 2) - 1, tr.data_list[i][j][0])
+                g9[f"data{i}_{name}_u8"] = u8
+        # record everything train() draws (trainer.py:197, models.py:621,580)
+        rec = {"s": [], "t": [], "noise": [], "loss": []}
+        real = {"multinomial": torch.multinomial, "randint": torch.randint, "randn_like": torch.randn_like}
+
+        def multinomial(*a, **k):
+            out = real["multinomial"](*a, **k)
+            rec["s"].append(int(out))
+            return out
+
+        def randint(*a, **k):
+            out = real["randint"](*a, **k)
+            rec["t"].append(out.clone())
+            return out
+
+        def randn_like(*a, **k):
+            out = real["randn_like"](*a, **k)
+            rec["noise"].append(out.clone())
+            return out
+        torch.multinomial, torch.randint, torch.randn_like = multinomial, randint, randn_like
+        import builtins
+        real_print = builtins.print
+
+        def tee(*a, **k):
+            msg = " ".join(str(x) for x in a)
+            if msg.startswith("step:"):
+                rec["loss"].append(msg)
+            real_print(*a, **k)
+        builtins.print = tee
+        try:
+            torch.manual_seed(100)
+            tr.train()
+        finally:
+            torch.multinomial, torch.randint, torch.randn_like = real["multinomial"], real["randint"], real["randn_like"]
+            builtins.print = real_print
+        assert len(rec["s"]) == 4 and len(rec["t"]) == 4 and len(rec["noise"]) == 4, {k: len(v) for k, v in rec.items()}
+        g9["s"] = np.array(rec["s"])
+        for i in range(4):
+            g9[f"t{i}"] = rec["t"][i].numpy()
+            g9[f"noise{i}"] = rec["noise"][i].numpy()
+        g9["running_loss"] = np.array(tr.running_loss, dtype=np.float64)
+        g9["lr_final"] = np.array(tr.scheduler.get_last_lr()[0])
+        g9["step_final"] = np.array(tr.step)
+        _store_grads(g9, "model", [(n, p.detach().clone().requires_grad_(False)) for n, p in tr.model.denoise_fn.named_parameters()])
+        _store_grads(g9, "ema", [(n, p.detach().clone().requires_grad_(False)) for n, p in tr.ema_model.denoise_fn.named_parameters()])
+        print("G9 scales drawn:", rec["s"], "running_loss:", tr.running_loss)
+    np.savez_compressed(OUT / "g9_trainer_steps.npz", **g9)
 
 
 if __name__ == "__main__":
