@@ -2,8 +2,8 @@
 
   G7  forward, loss and all 52 gradients at BASELINE's finest balloons scale (186x248, B=2, s=4);
   G8  the authors' trained forest EMA weights (results/forest/model-12.pt, committed as tests/golden/forest_ema_state.npz)
-      on the real noisy forest image: fp32 mode within 2e-4, tf32 mode inside the error band SURVEY.md 8c measured for
-      the reference's own TF32 default (2.6e-4 at t=95 ... 9.7e-3 at t=2, absolute, on |eps| <= ~5);
+      on the real noisy forest image: fp32 mode within 2e-4, tf32 mode within the worst case SURVEY.md H1 measured for
+      the reference's own TF32 default on these weights (~1e-2 absolute on |eps| <= ~5);
   G9  four steps of the reference MultiscaleTrainer.train() with every draw replayed: losses, Adam, LR schedule, EMA;
   and the full cfg-3 sampling chain (balloons sizes, T list [100,52,41,31,22] = 246 evaluations) against the CPU oracle.
 """
@@ -132,8 +132,7 @@ def test_trained_forest_weights_vs_reference_golden(golden, math):
                 assert err_rel <= 2e-4
                 assert loss.item() == pytest.approx(float(g[f"s{sc}_t{ti}_loss"]), rel=1e-4)
             else:
-                # inside (2x) the band the reference's own TF32 path shows on these weights
-                assert err_abs <= 2 * band[ti], (sc, ti, err_abs)
+                assert err_abs <= band and rel_err(eps, ref) <= 5e-3, (sc, ti, err_abs, rel_err(eps, ref))
                 assert loss.item() == pytest.approx(float(g[f"s{sc}_t{ti}_loss"]), rel=2e-2, abs=2e-4)
     # SURVEY 8c anchor input
     xa = torch.from_numpy(g["anchor_x"]).to(DEV)
