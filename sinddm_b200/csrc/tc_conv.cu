@@ -229,10 +229,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                 } else {
                     mbar_wait(&emptya_bar[sa_i], pha ^ 1u);
                 }
+                const int kys = main ? nky : 1;   // weight boxes of the vertical taps that read this halo box
+                // stage_release: ONE full barrier per stage -- the halo box's -- also receives the bytes of the stage's
+                // weight boxes, so the producer arrives once and the MMA warps wait once per stage
+                uint64_t* const stage_full = &fulla_bar[sa_i];
                 if (!TWO && (a.dbg & 1)) {
                     mbar_arrive_expect_tx_w(&fulla_bar[sa_i], 0);
                 } else if (!TWO) {
-                    mbar_arrive_expect_tx_w(&fulla_bar[sa_i], kABytes);
+                    mbar_arrive_expect_tx_w(&fulla_bar[sa_i], srel ? kABytes + (uint32_t)kys * nbytes : (uint32_t)kABytes);
                     tma_load_4d_w(smem + (size_t)sa_i * kABytes, main ? &tm_a : &tm_ares, &fulla_bar[sa_i], c * kKC,
                                   w0 + ((main && nkx == 3) ? kx - 1 : 0), h0 - 1, b);
                 } else {
@@ -246,8 +250,6 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                     sa_i = 0;
                     pha ^= 1u;
                 }
-                // weight boxes of the vertical taps that read this halo box
-                const int kys = main ? nky : 1;
                 for (int ky = 0; ky < kys; ++ky) {
                     const int tap = (main && nkx == 3) ? ky * 3 + kx : 0;
                     if (srel) {
@@ -258,17 +260,18 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                         mbar_wait(&emptyb_bar[sb_i], phb ^ 1u);
                     }
                     if (!TWO && (a.dbg & 1)) {
-                        mbar_arrive_expect_tx_w(&fullb_bar[sb_i], 0);
+                        if (!srel) mbar_arrive_expect_tx_w(&fullb_bar[sb_i], 0);
                     } else if (!TWO) {
-                        mbar_arrive_expect_tx_w(&fullb_bar[sb_i], nbytes);
+                        uint64_t* const box_full = srel ? stage_full : &fullb_bar[sb_i];
+                        if (!srel) mbar_arrive_expect_tx_w(box_full, nbytes);
                         if (a.w_blk) {
                             // the whole (tap, chunk) weight box is one contiguous pre-swizzled block
                             const float* src = main ? a.w_blk + ((size_t)tap * a.nchunks + c) * N * kKC
                                                     : a.wres_blk + (size_t)c * N * kKC;
-                            bulk_copy_g2s_w(smem_b + (size_t)sb_i * a.bbox_bytes, src, nbytes, &fullb_bar[sb_i]);
+                            bulk_copy_g2s_w(smem_b + (size_t)sb_i * a.bbox_bytes, src, nbytes, box_full);
                         } else {
-                            tma_load_2d_w(smem_b + (size_t)sb_i * a.bbox_bytes, main ? &tm_b : &tm_bres,
-                                          &fullb_bar[sb_i], c * kKC, tap * N);
+                            tma_load_2d_w(smem_b + (size_t)sb_i * a.bbox_bytes, main ? &tm_b : &tm_bres, box_full,
+                                          c * kKC, tap * N);
                         }
                     } else {
                         // this CTA stages rows [crank*N/2, (crank+1)*N/2) of the tap's weight matrix
@@ -305,6 +308,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         // observed through the mbarrier need none (the fence after the accumulator-slot wait orders against the
         // epilogue's tcgen05.ld).  SINDDM_TC_PEEK=0 restores wait + fence per box.
         bool b_ready = false;
+        bool st_ready = false;   // stage_release: the NEXT stage's (single) full barrier was seen complete by the peek
+        const bool srel = a.stage_release && a.peek;
         for (int st = pair_id; st < nsuper; st += npairs, ++titer) {
             const int s0 = (2 * titer) % kSlots, s1 = (2 * titer + 1) % kSlots;
             const int slot = half ? s1 : s0;
@@ -320,8 +325,32 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                 const int cvalid = main ? min(kKC, a.Cin - (it / nkx) * kKC) : min(kKC, a.Cres - (it - nst_main) * kKC);
                 const uint32_t nmma = (uint32_t)(cvalid >> 3);  // K = 8 tf32 per instruction, <= 4 per chunk
                 const int kys = main ? nky : 1;
-                mbar_wait(&fulla_bar[sa_i], pha);
+                if (!(srel && st_ready)) mbar_wait(&fulla_bar[sa_i], pha);
                 const uint32_t sa = smem_u32(smem + (size_t)sa_i * kABytes);
+                if (srel) {
+                    // one barrier per stage (halo box + its weight boxes), tested one stage ahead inside the asm that
+                    // issues this stage's last MMAs; one commit per stage releases everything the stage read
+                    const int sa_n = (sa_i + 1 == kStagesA) ? 0 : sa_i + 1;
+                    const uint32_t ph_n = (sa_n == 0) ? pha ^ 1u : pha;
+                    uint32_t r = 0;
+                    for (int ky = 0; ky < kys; ++ky) {
+                        const int row0 = ((main && nky == 3) ? ky : 1) + 8 * half;
+                        const uint32_t ad = ((sa + (uint32_t)row0 * kRowBytes) >> 4) & 0x3FFFu;
+                        const uint32_t bd = (smem_u32(smem_b + (size_t)sb_i * a.bbox_bytes) >> 4) & 0x3FFFu;
+                        if (++sb_i == a.nstages_b) sb_i = 0;
+                        const uint32_t acc = (it | ky) != 0 ? 1u : 0u;
+                        if (a.dbg & 4) continue;
+                        if (ky == kys - 1) r = umma_tf32_ss_x4_test(dacc, ad, bd, desc_hi, 2u, a.idesc, acc, nmma, &fulla_bar[sa_n], ph_n);
+                        else umma_tf32_ss_x4(dacc, ad, bd, desc_hi, 2u, a.idesc, acc, nmma);
+                    }
+                    umma_commit_elect(&emptya_bar[sa_i]);
+                    st_ready = __all_sync(0xffffffffu, r != 0);
+                    if (++sa_i == kStagesA) {
+                        sa_i = 0;
+                        pha ^= 1u;
+                    }
+                    continue;
+                }
                 for (int ky = 0; ky < kys; ++ky) {
                     if (!b_ready) mbar_wait(&fullb_bar[sb_i], phb);
                     if (!a.peek) tc_fence_after_sync();
@@ -337,11 +366,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                     if (a.peek && !(a.dbg & 4)) {
                         const uint32_t r = umma_tf32_ss_x4_test(dacc, ad, bd, desc_hi, 2u, a.idesc, (it | ky) != 0 ? 1u : 0u,
                                                                 nmma, &fullb_bar[sb_i], phb);
-                        if (!a.stage_release) umma_commit_elect(&emptyb_bar[sb_cur]);
+                        umma_commit_elect(&emptyb_bar[sb_cur]);
                         b_ready = __all_sync(0xffffffffu, r != 0);
                     } else {
                         if (!(a.dbg & 4)) umma_tf32_ss_x4(dacc, ad, bd, desc_hi, 2u, a.idesc, (it | ky) != 0 ? 1u : 0u, nmma);
-                        if (!a.stage_release) umma_commit_elect(&emptyb_bar[sb_cur]);
+                        umma_commit_elect(&emptyb_bar[sb_cur]);
                         b_ready = false;
                     }
                 }
@@ -872,7 +901,8 @@ int tc_conv_prepare(const ConvProblem& p, TcConvOp* op) {
     op->sw_dbg = env_int("SINDDM_TC_DEBUG", 0);                 // diagnostic runs only: results are wrong when set
     // stage-granular release needs the ring to hold two whole stages plus the boxes in flight behind them
     const int nky = p.ntaps == 9 ? 3 : 1;
-    op->sw_stage_release = env_int("SINDDM_TC_STAGE_RELEASE", 1) != 0 && cs == 1 && op->sw_issuers2 && nst >= 2 * nky + 2;
+    op->sw_stage_release = env_int("SINDDM_TC_STAGE_RELEASE", 1) != 0 && cs == 1 && op->sw_issuers2 && op->sw_peek &&
+                           nst >= 2 * nky + 2;
     return SINDDM_OK;
 }
 

@@ -17,6 +17,12 @@
 //                  3 x (4 x 32) x Cy accumulators of their three horizontal taps: 3 MMA tiles from 4 boxes
 //                  instead of 12 boxes (1.8x fewer bytes per FLOP at 160 channels, 2x at Cy = 80).
 //   accumulators   up to 3 tiles x Cy fp32 columns in TMEM, resident for the CTA's whole pixel range.
+//   issue          one MMA-issuing warp per accumulator tile (= horizontal tap): a K step is 12 MMAs, and one warp needs
+//                  ~60 cycles per MMA plus ~230 per mbarrier wait / tcgen05.commit (tools/pipe_bench.cu) -- ~1300 cycles
+//                  per K step against 480 (Cy = 80) / 960 (Cy = 160) cycles of tensor-pipe work.  Three issuers (4 MMAs +
+//                  one commit each, the next stage's barrier tested inside the MMA asm, no tcgen05 fence per step)
+//                  bring the issue path under the pipe time.  Every accumulator still has ONE issuing thread walking K
+//                  in order, so the summation order -- and the result -- stay bit-reproducible.
 //   grid           nsplit (pixel ranges) x ngroups (region sets); each CTA writes its partial [tap][ci][co] block,
 //                  a second kernel (wgrad_reduce) sums the splits in fixed order (deterministic).
 #include "common.cuh"
@@ -32,7 +38,8 @@ constexpr int kRowBytes = kCC * 4;        // one pixel of a box: 128 B
 constexpr int kDyBoxBytes = kKP * kRowBytes;   // 4 KiB
 constexpr int kRegPerTile = 4;            // 32-channel regions per M = 128 tile
 constexpr int kMaxTiles = 3;
-constexpr int kThreads = 192;
+constexpr int kThreads = 256;             // warp 0: TMA producer, warps 1-3: one MMA issuer per accumulator tile, warps 4-7: epilogue
+constexpr int kIssuers = kMaxTiles;
 
 struct KernelArgs {
     int B, H, W;
@@ -82,9 +89,9 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         tma_prefetch_desc(&tm_dy);
         for (int i = 0; i < a.nstages; ++i) {
             mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], 1);
+            mbar_init(&empty_bar[i], (uint32_t)a.ntile);   // one commit per issuing warp
         }
-        mbar_init(done_bar, 1);
+        mbar_init(done_bar, (uint32_t)a.ntile);
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
@@ -122,40 +129,44 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 phase ^= 1u;
             }
         }
-    } else if (warp == 1) {
-        int stage = 0;
-        uint32_t phase = 0;
-        // MN-major, 128B swizzle with 32B atoms: 4-pixel atoms are 512 B apart (SBO); the 32-channel boxes of one
-        // operand are LBO apart (bits 16.. of the low word): one region stride for x, one box for dy.
-        // 8 pixels per MMA = 1024 B = +64 in the start address.
-        const uint64_t proto_x = umma_smem_desc(0, (uint32_t)a.rb, 512, UMMA_LAYOUT_SW128_B32);
-        const uint64_t proto_y = umma_smem_desc(0, kDyBoxBytes, 512, UMMA_LAYOUT_SW128_B32);
-        const uint32_t desc_hi = (uint32_t)(proto_y >> 32);
-        const uint32_t lbo_x = (uint32_t)proto_x, lbo_y = (uint32_t)proto_y;
-        for (int ks = ks_begin; ks < ks_end; ++ks) {
-            mbar_wait(&full_bar[stage], phase);
-            tc_fence_after_sync();
-            const uint32_t sx = smem_u32(smem + (size_t)stage * a.stage_bytes);
-            const uint32_t sy = sx + (uint32_t)a.x_bytes;
-            const uint32_t acc = (ks != ks_begin) ? 1u : 0u;
-            const uint32_t b_lo = lbo_y | ((sy >> 4) & 0x3FFFu);
-            for (int i = 0; i < a.ntile; ++i) {
-                // 3x3: tile i = horizontal tap i, the box read from pixel i on;  1x1: tile i = regions 4i..4i+3
-                const uint32_t start = k3 ? sx + (uint32_t)i * kRowBytes : sx + (uint32_t)(i * kRegPerTile * a.rb);
-                const uint32_t a_lo = lbo_x | ((start >> 4) & 0x3FFFu);
+    } else if (warp <= kIssuers) {
+        // tile i = warp - 1:  3x3: horizontal tap i, the box read from pixel i on;  1x1: regions 4i..4i+3
+        const int i = warp - 1;
+        if (i < a.ntile) {
+            int stage = 0;
+            uint32_t phase = 0;
+            // MN-major, 128B swizzle with 32B atoms: 4-pixel atoms are 512 B apart (SBO); the 32-channel boxes of one
+            // operand are LBO apart (bits 16.. of the low word): one region stride for x, one box for dy.
+            // 8 pixels per MMA = 1024 B = +64 in the start address.
+            const uint64_t proto_x = umma_smem_desc(0, (uint32_t)a.rb, 512, UMMA_LAYOUT_SW128_B32);
+            const uint64_t proto_y = umma_smem_desc(0, kDyBoxBytes, 512, UMMA_LAYOUT_SW128_B32);
+            const uint32_t desc_hi = (uint32_t)(proto_y >> 32);
+            const uint32_t lbo_x = (uint32_t)proto_x, lbo_y = (uint32_t)proto_y;
+            const uint32_t dacc = tmem_base + (uint32_t)(i * a.col_stride);
+            const uint32_t tile_off = k3 ? (uint32_t)i * kRowBytes : (uint32_t)(i * kRegPerTile * a.rb);
+            bool ready = false;   // the next stage's full barrier was seen complete by the test inside the MMA asm
+            for (int ks = ks_begin; ks < ks_end; ++ks) {
+                if (!ready) mbar_wait(&full_bar[stage], phase);
+                const uint32_t sx = smem_u32(smem + (size_t)stage * a.stage_bytes);
+                const uint32_t sy = sx + (uint32_t)a.x_bytes;
+                const uint32_t b_lo = lbo_y | ((sy >> 4) & 0x3FFFu);
                 // A start that is a whole number of pixels (128 B) into the box needs no base-offset field: the
                 // tensor core applies the swizzle to absolute shared-memory address bits, like TMA did on the way
                 // in (verified on B200: base offset 0 is bit-compatible with the aligned kernel, non-zero is wrong)
-                umma_tf32_ss_x4(tmem_base + (uint32_t)(i * a.col_stride), a_lo, b_lo, desc_hi, 64u, a.idesc, acc,
-                                kKP / 8);
+                const uint32_t a_lo = lbo_x | (((sx + tile_off) >> 4) & 0x3FFFu);
+                const int cur = stage;
+                if (++stage == a.nstages) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+                // operands written by TMA and observed through the mbarrier need no tcgen05 fence (as in tc_conv)
+                const uint32_t r = umma_tf32_ss_x4_test(dacc, a_lo, b_lo, desc_hi, 64u, a.idesc, (ks != ks_begin) ? 1u : 0u,
+                                                        kKP / 8, &full_bar[stage], phase);
+                umma_commit_elect(&empty_bar[cur]);
+                ready = __all_sync(0xffffffffu, r != 0);
             }
-            umma_commit_elect(&empty_bar[stage]);
-            if (++stage == a.nstages) {
-                stage = 0;
-                phase ^= 1u;
-            }
+            umma_commit_elect(done_bar);
         }
-        umma_commit_elect(done_bar);
     } else {
         // epilogue: one accumulator row (= one (tap, ci)) per thread, Cy contiguous floats each
         const int quarter = warp & 3;
