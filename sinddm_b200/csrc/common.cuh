@@ -446,6 +446,92 @@ SINDDM_DEVINL uint32_t umma_tf32_ss_x4_test(uint32_t tmem_d, uint32_t a_lo, uint
     return ready;
 }
 
+// Variants with separate high descriptor words for A (hi) and B (hi_b): operands whose core-group strides differ.
+SINDDM_DEVINL void umma_tf32_ss_x4_h2(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t hi_b, uint32_t step_lo,
+                                   uint32_t idesc, uint32_t acc_first, uint32_t nk) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pe, pacc, pone, p1, p2, p3;\n\t"
+        ".reg .b32 rx, a1, a2, a3, b1, b2, b3;\n\t"
+        ".reg .b64 da0, da1, da2, da3, db0, db1, db2, db3;\n\t"
+        "elect.sync rx|pe, 0xffffffff;\n\t"
+        "setp.ne.b32 pacc, %6, 0;\n\t"
+        "setp.eq.b32 pone, 0, 0;\n\t"
+        "setp.gt.u32 p1, %7, 1;\n\t"
+        "setp.gt.u32 p2, %7, 2;\n\t"
+        "setp.gt.u32 p3, %7, 3;\n\t"
+        "and.pred p1, p1, pe;\n\t"
+        "and.pred p2, p2, pe;\n\t"
+        "and.pred p3, p3, pe;\n\t"
+        "add.u32 a1, %1, %4;\n\t"
+        "add.u32 a2, a1, %4;\n\t"
+        "add.u32 a3, a2, %4;\n\t"
+        "add.u32 b1, %2, %4;\n\t"
+        "add.u32 b2, b1, %4;\n\t"
+        "add.u32 b3, b2, %4;\n\t"
+        "mov.b64 da0, {%1, %3};\n\t"
+        "mov.b64 da1, {a1, %3};\n\t"
+        "mov.b64 da2, {a2, %3};\n\t"
+        "mov.b64 da3, {a3, %3};\n\t"
+        "mov.b64 db0, {%2, %8};\n\t"
+        "mov.b64 db1, {b1, %8};\n\t"
+        "mov.b64 db2, {b2, %8};\n\t"
+        "mov.b64 db3, {b3, %8};\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], da0, db0, %5, pacc;\n\t"
+        "@p1 tcgen05.mma.cta_group::1.kind::tf32 [%0], da1, db1, %5, pone;\n\t"
+        "@p2 tcgen05.mma.cta_group::1.kind::tf32 [%0], da2, db2, %5, pone;\n\t"
+        "@p3 tcgen05.mma.cta_group::1.kind::tf32 [%0], da3, db3, %5, pone;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(hi), "r"(step_lo), "r"(idesc), "r"(acc_first), "r"(nk), "r"(hi_b)
+        : "memory");
+}
+
+SINDDM_DEVINL uint32_t umma_tf32_ss_x4_test_h2(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t hi_b, uint32_t step_lo,
+                                            uint32_t idesc, uint32_t acc_first, uint32_t nk, uint64_t* next_bar,
+                                            uint32_t next_parity) {
+    uint32_t ready;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pe, pacc, pone, p1, p2, p3, pnext;\n\t"
+        ".reg .b32 rx, a1, a2, a3, b1, b2, b3;\n\t"
+        ".reg .b64 da0, da1, da2, da3, db0, db1, db2, db3;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 pnext, [%9], %10;\n\t"
+        "elect.sync rx|pe, 0xffffffff;\n\t"
+        "setp.ne.b32 pacc, %7, 0;\n\t"
+        "setp.eq.b32 pone, 0, 0;\n\t"
+        "setp.gt.u32 p1, %8, 1;\n\t"
+        "setp.gt.u32 p2, %8, 2;\n\t"
+        "setp.gt.u32 p3, %8, 3;\n\t"
+        "and.pred p1, p1, pe;\n\t"
+        "and.pred p2, p2, pe;\n\t"
+        "and.pred p3, p3, pe;\n\t"
+        "add.u32 a1, %2, %5;\n\t"
+        "add.u32 a2, a1, %5;\n\t"
+        "add.u32 a3, a2, %5;\n\t"
+        "add.u32 b1, %3, %5;\n\t"
+        "add.u32 b2, b1, %5;\n\t"
+        "add.u32 b3, b2, %5;\n\t"
+        "mov.b64 da0, {%2, %4};\n\t"
+        "mov.b64 da1, {a1, %4};\n\t"
+        "mov.b64 da2, {a2, %4};\n\t"
+        "mov.b64 da3, {a3, %4};\n\t"
+        "mov.b64 db0, {%3, %11};\n\t"
+        "mov.b64 db1, {b1, %11};\n\t"
+        "mov.b64 db2, {b2, %11};\n\t"
+        "mov.b64 db3, {b3, %11};\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], da0, db0, %6, pacc;\n\t"
+        "@p1 tcgen05.mma.cta_group::1.kind::tf32 [%1], da1, db1, %6, pone;\n\t"
+        "@p2 tcgen05.mma.cta_group::1.kind::tf32 [%1], da2, db2, %6, pone;\n\t"
+        "@p3 tcgen05.mma.cta_group::1.kind::tf32 [%1], da3, db3, %6, pone;\n\t"
+        "selp.u32 %0, 1, 0, pnext;\n\t"
+        "}\n"
+        : "=r"(ready)
+        : "r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(step_lo), "r"(idesc), "r"(acc_first), "r"(nk),
+          "r"(smem_u32(next_bar)), "r"(next_parity), "r"(hi_b)
+        : "memory");
+    return ready;
+}
+
 // Whole-warp version of umma_commit: one elected lane arrives.
 SINDDM_DEVINL void umma_commit_elect(uint64_t* bar) {
     asm volatile(

@@ -59,7 +59,17 @@ constexpr int kEpiWarp0 = 4;        // roles are warpgroup aligned so that setma
 constexpr int kEpiThreads = 256;
 constexpr int kTmemCols = 512;
 constexpr int kSlots = 3;
-constexpr int kStagesA = 3;   // activation (halo box) ring
+constexpr int kStagesA = 3;   // activation (halo box) ring (halo mode: 2 slots of the larger box)
+// "halo" mode (3x3 layers): ONE (32 ch, 18 w, 18 h) box per channel chunk serves all nine taps -- tap (ky, kx) of the
+// M = 128 half tile hf (16 rows x 8 pixels) is the same box read from pixel (ky * 18 + kx + 8 * hf) on, 8-pixel core
+// groups one box row (18 x 128 B) apart: the start address moves by whole pixels (128 B), the swizzle pattern TMA wrote
+// and the tensor core reads are both functions of the absolute shared-memory address.  Activation bytes entering
+// shared memory drop 2.6x (3 x 36 KiB -> 40.5 KiB per chunk); the kernel was bound by exactly those bytes.
+constexpr int kHaloBW = kTileW + 2;                              // box width in pixels
+constexpr int kHaloPitch = kHaloBW * kKC * 4;                    // 2304 B between image rows of the box
+constexpr int kHaloBoxBytes = kBoxH * kHaloPitch;                // 41472 B
+constexpr int kHaloSlotBytes = (kHaloBoxBytes + 1023) / 1024 * 1024;
+constexpr int kHaloStagesA = 2;
 constexpr int kMaxStagesB = 8;   // weight box ring
 // epilogue staging: every epilogue warp owns two [32 px][16 ch] tiles (64B-swizzled, 2 KiB).  Layers that stream an
 // operand in (residual / saved pre-activation) have one result: tile 0 receives the TMA load, tile 1 is drained by
@@ -82,6 +92,8 @@ struct KernelArgs {
     uint32_t idesc;
     int issuers2;              // single-CTA kernel: warps 1 and 2 each issue the MMAs of one half tile (SINDDM_TC_ISSUERS=1: warp 1 issues both)
     int peek;                  // MMA warps test the next weight box's barrier inside the MMA asm, no per-box tcgen05 fence (SINDDM_TC_PEEK=0: off)
+    int halo;                  // one halo box per chunk for all nine taps (see kHaloBW); M halves split the tile by columns
+    int nsa, abytes, atx;      // activation ring: slots, bytes between slots, bytes per box
     int stage_release;         // narrow layers (weight ring >= 2 2/3 stages): the MMA warps commit ONE barrier per stage (the
                                // halo box's empty barrier) that also releases the stage's weight boxes, instead of
                                // one commit per box -- every tcgen05.commit costs its warp ~230 cycles, as long as the
@@ -108,7 +120,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
-    uint8_t* smem_b = smem + (size_t)kStagesA * kABytes;
+    uint8_t* smem_b = smem + (size_t)a.nsa * a.abytes;
     uint8_t* smem_epi = smem_b + (size_t)a.nstages_b * a.bbox_bytes;
     uint8_t* tail = smem_epi + kEpiBytes;
     uint64_t* fulla_bar = reinterpret_cast<uint64_t*>(tail);
@@ -138,7 +150,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             if (!a.w_blk) tma_prefetch_desc(&tm_bres);
         }
         // empty barriers: one commit per MMA-issuing warp (two in the single-CTA kernel, see below)
-        for (int i = 0; i < kStagesA; ++i) {
+        for (int i = 0; i < a.nsa; ++i) {
             mbar_init(&fulla_bar[i], TWO ? 2 : 1);   // one arrival per producing CTA
             mbar_init(&emptya_bar[i], (!TWO && a.issuers2) ? 2 : 1);
         }
@@ -179,8 +191,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     const int npairs = gridDim.x / CS;
     const int nsuper = (a.ntiles + CS - 1) / CS;
 
-    const int nkx = a.ntaps == 9 ? 3 : 1;           // horizontal taps = stages per chunk
-    const int nky = nkx;                             // vertical taps = weight boxes per stage
+    const bool halo = !TWO && a.halo;
+    const int nkx = (a.ntaps == 9 && !halo) ? 3 : 1; // stages per chunk: one per horizontal tap (halo mode: one)
+    const int nky = a.ntaps == 9 ? (halo ? 9 : 3) : 1;   // weight boxes per stage: vertical taps (halo mode: all nine)
     const int nst_main = a.nchunks * nkx;
     const int nst = nst_main + a.nchunks_res;        // stages per tile
     const uint32_t nbytes = (uint32_t)(N / CS) * kKC * 4;   // one weight box as staged by THIS CTA
@@ -204,7 +217,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             mbar_wait(&emptya_bar[rel_slot], rel_par);
             rel_boxes += (rel_local < nst_main) ? nky : 1;
             if (++rel_local == nst) rel_local = 0;
-            if (++rel_slot == kStagesA) {
+            if (++rel_slot == a.nsa) {
                 rel_slot = 0;
                 rel_par ^= 1u;
             }
@@ -224,7 +237,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                 const int kx = main ? it - c * nkx : 0;
                 // activation halo box: rows h0-1 .. h0+16, columns shifted by the horizontal tap
                 if (srel) {
-                    while (rel < jst - kStagesA + 1) release_one();
+                    while (rel < jst - a.nsa + 1) release_one();
                     ++jst;
                 } else {
                     mbar_wait(&emptya_bar[sa_i], pha ^ 1u);
@@ -236,9 +249,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                 if (!TWO && (a.dbg & 1)) {
                     mbar_arrive_expect_tx_w(&fulla_bar[sa_i], 0);
                 } else if (!TWO) {
-                    mbar_arrive_expect_tx_w(&fulla_bar[sa_i], srel ? kABytes + (uint32_t)kys * nbytes : (uint32_t)kABytes);
-                    tma_load_4d_w(smem + (size_t)sa_i * kABytes, main ? &tm_a : &tm_ares, &fulla_bar[sa_i], c * kKC,
-                                  w0 + ((main && nkx == 3) ? kx - 1 : 0), h0 - 1, b);
+                    mbar_arrive_expect_tx_w(&fulla_bar[sa_i], srel ? (uint32_t)a.atx + (uint32_t)kys * nbytes : (uint32_t)a.atx);
+                    tma_load_4d_w(smem + (size_t)sa_i * a.abytes, main ? &tm_a : &tm_ares, &fulla_bar[sa_i], c * kKC,
+                                  halo ? w0 - 1 : w0 + ((main && nkx == 3) ? kx - 1 : 0), h0 - 1, b);
                 } else {
                     // both CTAs' boxes complete on the LEADER's barrier, which expects the bytes of both
                     if (crank == 0) mbar_arrive_expect_tx_w(&fulla_bar[sa_i], 2 * kABytes);
@@ -246,12 +259,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                     tma_load_4d_2sm_w(smem + (size_t)sa_i * kABytes, main ? &tm_a : &tm_ares, &fulla_bar[sa_i], c * kKC,
                                       w0 + ((main && nkx == 3) ? kx - 1 : 0), h0 - 1, b);
                 }
-                if (++sa_i == kStagesA) {
+                if (++sa_i == a.nsa) {
                     sa_i = 0;
                     pha ^= 1u;
                 }
                 for (int ky = 0; ky < kys; ++ky) {
-                    const int tap = (main && nkx == 3) ? ky * 3 + kx : 0;
+                    const int tap = !main ? 0 : halo ? ky : (nkx == 3 ? ky * 3 + kx : 0);
                     if (srel) {
                         // slot kbox % nstages_b was last used by box kbox - nstages_b: its whole stage must be done
                         while (rel_boxes < kbox - a.nstages_b + 1) release_one();
@@ -300,7 +313,18 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         uint32_t pha = 0, phb = 0;
         uint32_t slot_uses[kSlots] = {0, 0, 0};
         int titer = 0;
-        const uint32_t desc_hi = (uint32_t)(umma_smem_desc(0, 0, 1024, UMMA_LAYOUT_SW128) >> 32);
+        // high words of the operand descriptors: 8-pixel core groups are 1024 B apart (16-pixel box rows: contiguous) or,
+        // in halo mode, one 18-pixel box row apart; weight boxes are dense [N][128 B]
+        const uint32_t desc_hi_b = (uint32_t)(umma_smem_desc(0, 0, 1024, UMMA_LAYOUT_SW128) >> 32);
+        const uint32_t desc_hi = halo ? (uint32_t)(umma_smem_desc(0, 0, kHaloPitch, UMMA_LAYOUT_SW128) >> 32) : desc_hi_b;
+        // byte offset of this half's operand inside the activation box for vertical tap / box index ky
+        auto a_off = [&](bool main, int ky) -> uint32_t {
+            if (halo) {
+                const int ty = main ? ky / 3 : 1, tx = main ? ky - 3 * (ky / 3) : 1;
+                return (uint32_t)((ty * kHaloBW + tx + 8 * half) * (kKC * 4));
+            }
+            return (uint32_t)((((main && nky == 3) ? ky : 1) + 8 * half) * kRowBytes);
+        };
         // Every barrier / tcgen05 bookkeeping instruction stalls this warp for 180-260 cycles (tools/pipe_bench.cu),
         // about as long as the four N = 80 MMAs of a weight box execute.  So the NEXT box's full barrier is tested
         // inside the asm that issues the current box's MMAs (the answer is read after the MMAs were issued;
@@ -326,26 +350,25 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                 const uint32_t nmma = (uint32_t)(cvalid >> 3);  // K = 8 tf32 per instruction, <= 4 per chunk
                 const int kys = main ? nky : 1;
                 if (!(srel && st_ready)) mbar_wait(&fulla_bar[sa_i], pha);
-                const uint32_t sa = smem_u32(smem + (size_t)sa_i * kABytes);
+                const uint32_t sa = smem_u32(smem + (size_t)sa_i * a.abytes);
                 if (srel) {
                     // one barrier per stage (halo box + its weight boxes), tested one stage ahead inside the asm that
                     // issues this stage's last MMAs; one commit per stage releases everything the stage read
-                    const int sa_n = (sa_i + 1 == kStagesA) ? 0 : sa_i + 1;
+                    const int sa_n = (sa_i + 1 == a.nsa) ? 0 : sa_i + 1;
                     const uint32_t ph_n = (sa_n == 0) ? pha ^ 1u : pha;
                     uint32_t r = 0;
                     for (int ky = 0; ky < kys; ++ky) {
-                        const int row0 = ((main && nky == 3) ? ky : 1) + 8 * half;
-                        const uint32_t ad = ((sa + (uint32_t)row0 * kRowBytes) >> 4) & 0x3FFFu;
+                        const uint32_t ad = ((sa + a_off(main, ky)) >> 4) & 0x3FFFu;
                         const uint32_t bd = (smem_u32(smem_b + (size_t)sb_i * a.bbox_bytes) >> 4) & 0x3FFFu;
                         if (++sb_i == a.nstages_b) sb_i = 0;
                         const uint32_t acc = (it | ky) != 0 ? 1u : 0u;
                         if (a.dbg & 4) continue;
-                        if (ky == kys - 1) r = umma_tf32_ss_x4_test(dacc, ad, bd, desc_hi, 2u, a.idesc, acc, nmma, &fulla_bar[sa_n], ph_n);
-                        else umma_tf32_ss_x4(dacc, ad, bd, desc_hi, 2u, a.idesc, acc, nmma);
+                        if (ky == kys - 1) r = umma_tf32_ss_x4_test_h2(dacc, ad, bd, desc_hi, desc_hi_b, 2u, a.idesc, acc, nmma, &fulla_bar[sa_n], ph_n);
+                        else umma_tf32_ss_x4_h2(dacc, ad, bd, desc_hi, desc_hi_b, 2u, a.idesc, acc, nmma);
                     }
                     umma_commit_elect(&emptya_bar[sa_i]);
                     st_ready = __all_sync(0xffffffffu, r != 0);
-                    if (++sa_i == kStagesA) {
+                    if (++sa_i == a.nsa) {
                         sa_i = 0;
                         pha ^= 1u;
                     }
@@ -355,8 +378,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                     if (!b_ready) mbar_wait(&fullb_bar[sb_i], phb);
                     if (!a.peek) tc_fence_after_sync();
                     // vertical tap = row offset into the halo box; the 1x1 / residual case reads the centre rows
-                    const int row0 = ((main && nky == 3) ? ky : 1) + 8 * half;
-                    const uint32_t ad = ((sa + (uint32_t)row0 * kRowBytes) >> 4) & 0x3FFFu;
+                    const uint32_t ad = ((sa + a_off(main, ky)) >> 4) & 0x3FFFu;
                     const uint32_t bd = (smem_u32(smem_b + (size_t)sb_i * a.bbox_bytes) >> 4) & 0x3FFFu;
                     const int sb_cur = sb_i;
                     if (++sb_i == a.nstages_b) {
@@ -364,18 +386,18 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                         phb ^= 1u;
                     }
                     if (a.peek && !(a.dbg & 4)) {
-                        const uint32_t r = umma_tf32_ss_x4_test(dacc, ad, bd, desc_hi, 2u, a.idesc, (it | ky) != 0 ? 1u : 0u,
-                                                                nmma, &fullb_bar[sb_i], phb);
+                        const uint32_t r = umma_tf32_ss_x4_test_h2(dacc, ad, bd, desc_hi, desc_hi_b, 2u, a.idesc,
+                                                                   (it | ky) != 0 ? 1u : 0u, nmma, &fullb_bar[sb_i], phb);
                         umma_commit_elect(&emptyb_bar[sb_cur]);
                         b_ready = __all_sync(0xffffffffu, r != 0);
                     } else {
-                        if (!(a.dbg & 4)) umma_tf32_ss_x4(dacc, ad, bd, desc_hi, 2u, a.idesc, (it | ky) != 0 ? 1u : 0u, nmma);
+                        if (!(a.dbg & 4)) umma_tf32_ss_x4_h2(dacc, ad, bd, desc_hi, desc_hi_b, 2u, a.idesc, (it | ky) != 0 ? 1u : 0u, nmma);
                         umma_commit_elect(&emptyb_bar[sb_cur]);
                         b_ready = false;
                     }
                 }
                 umma_commit_elect(&emptya_bar[sa_i]);
-                if (++sa_i == kStagesA) {
+                if (++sa_i == a.nsa) {
                     sa_i = 0;
                     pha ^= 1u;
                 }
@@ -548,8 +570,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 #pragma unroll 1
             for (int half = 0; half < 2; ++half) {
                 const int slot = (2 * titer + half) % kSlots;
-                const int h = th * kTileH + half * 8 + row / kTileW, w = tw * kTileW + row % kTileW;
-                const int hq = th * kTileH + half * 8 + quarter * 2, w0 = tw * kTileW;   // this warp's strip
+                // accumulator row -> pixel.  Stacked halves: half = 8 image rows x 16 px, this warp's strip = 2 rows x 16 px;
+                // halo mode: half = 16 rows x 8 px (columns 8*half ..), this warp's strip = 4 rows x 8 px
+                const int h = halo ? th * kTileH + (row >> 3) : th * kTileH + half * 8 + row / kTileW;
+                const int w = halo ? tw * kTileW + half * 8 + (row & 7) : tw * kTileW + row % kTileW;
+                const int hq = halo ? th * kTileH + quarter * 4 : th * kTileH + half * 8 + quarter * 2;
+                const int w0 = halo ? tw * kTileW + half * 8 : tw * kTileW;   // this warp's strip
                 const bool valid = live && (h < a.H) && (w < a.W);
                 const size_t pix = ((size_t)b * a.H + h) * a.W + w;
                 const unsigned vmask = ep.colsum_part ? __ballot_sync(0xffffffffu, valid) : 0u;
@@ -849,11 +875,21 @@ int tc_conv_prepare(const ConvProblem& p, TcConvOp* op) {
     // CTA pairs (SINDDM_TC_2SM=0 disables): each CTA stages N/2 weight rows, which must be whole 8-row atoms
     op->cs = (two_sm_setting() && p.N % 16 == 0 && !p.w_blocked) ? 2 : 1;
     const int cs = op->cs;
-    SINDDM_TRY(make_tmap_nhwc(&op->tm_a, p.in, p.B, p.H, p.W, p.Cin, kKC, kTileW, kBoxH, CU_TENSOR_MAP_SWIZZLE_128B));
+    // halo mode: 3x3 layers of the single-CTA kernel (SINDDM_TC_HALO=0: the three-boxes-per-chunk walk)
+    {
+        const char* e = getenv("SINDDM_TC_HALO");
+        const char* ei = getenv("SINDDM_TC_ISSUERS");      // the halo walk lives in the two-issuer loop
+        op->halo = (p.ntaps == 9 && cs == 1 && !(e && atoi(e) == 0) && !(ei && atoi(ei) == 1)) ? 1 : 0;
+    }
+    const int abw = op->halo ? kHaloBW : kTileW;       // activation box width in pixels
+    op->nsa = op->halo ? kHaloStagesA : kStagesA;
+    op->abytes = op->halo ? kHaloSlotBytes : kABytes;
+    op->atx = op->halo ? kHaloBoxBytes : kABytes;
+    SINDDM_TRY(make_tmap_nhwc(&op->tm_a, p.in, p.B, p.H, p.W, p.Cin, kKC, abw, kBoxH, CU_TENSOR_MAP_SWIZZLE_128B));
     if (p.w_blocked) memset(&op->tm_b, 0, sizeof(op->tm_b));
     else SINDDM_TRY(make_tmap_2d(&op->tm_b, p.w, p.Cin, p.ntaps * p.N, kKC, p.N / cs, CU_TENSOR_MAP_SWIZZLE_128B));
     if (p.in_res) {
-        SINDDM_TRY(make_tmap_nhwc(&op->tm_ares, p.in_res, p.B, p.H, p.W, p.Cres, kKC, kTileW, kBoxH,
+        SINDDM_TRY(make_tmap_nhwc(&op->tm_ares, p.in_res, p.B, p.H, p.W, p.Cres, kKC, abw, kBoxH,
                                   CU_TENSOR_MAP_SWIZZLE_128B));
         if (p.w_blocked) memset(&op->tm_bres, 0, sizeof(op->tm_bres));
         else SINDDM_TRY(make_tmap_2d(&op->tm_bres, p.w_res, p.Cres, p.N, kKC, p.N / cs, CU_TENSOR_MAP_SWIZZLE_128B));
@@ -868,8 +904,8 @@ int tc_conv_prepare(const ConvProblem& p, TcConvOp* op) {
         CUtensorMap* maps[3] = {&op->tm_out, &op->tm_pre, &op->tm_in};
         for (int i = 0; i < 3; ++i) {
             if (ptrs[i])
-                SINDDM_TRY(make_tmap_nhwc(maps[i], ptrs[i], p.B, p.H, p.W, p.N, kEpiChunk, kTileW, 2,
-                                          CU_TENSOR_MAP_SWIZZLE_64B));
+                SINDDM_TRY(make_tmap_nhwc(maps[i], ptrs[i], p.B, p.H, p.W, p.N, kEpiChunk, op->halo ? 8 : kTileW,
+                                          op->halo ? 4 : 2, CU_TENSOR_MAP_SWIZZLE_64B));
             else
                 *maps[i] = op->tm_a;
         }
@@ -877,12 +913,12 @@ int tc_conv_prepare(const ConvProblem& p, TcConvOp* op) {
     // weight ring: as many boxes as fit beside the 3 activation slots and the epilogue tiles (at most kMaxStagesB)
     op->stage_bytes = (int)align_up((size_t)(p.N / cs) * kKC * 4, 1024);
     const int budget =
-        device_info().max_smem_optin - 1024 /*alignment slack*/ - kTailBytes - kStagesA * kABytes - kEpiBytes;
+        device_info().max_smem_optin - 1024 /*alignment slack*/ - kTailBytes - op->nsa * op->abytes - kEpiBytes;
     int nst = budget / op->stage_bytes;
     if (nst > kMaxStagesB) nst = kMaxStagesB;
     SINDDM_REQUIRE(nst >= 3, "tc_conv: not enough shared memory for the weight ring");
     op->nstages = nst;
-    op->smem_bytes = kStagesA * kABytes + nst * op->stage_bytes + kEpiBytes + kTailBytes + 1024;
+    op->smem_bytes = op->nsa * op->abytes + nst * op->stage_bytes + kEpiBytes + kTailBytes + 1024;
     op->tiles_w = ceil_div(p.W, kTileW);
     op->tiles_h = ceil_div(p.H, kTileH);
     op->ntiles = op->tiles_w * op->tiles_h * p.B;
@@ -896,11 +932,11 @@ int tc_conv_prepare(const ConvProblem& p, TcConvOp* op) {
         return e ? atoi(e) : dflt;
     };
     op->sw_peek = env_int("SINDDM_TC_PEEK", 1) != 0;
-    op->sw_l2pf = env_int("SINDDM_TC_L2PF", 0) != 0;            // measured neutral (profiles/): off unless asked for
+    op->sw_l2pf = env_int("SINDDM_TC_L2PF", 0) != 0 && !op->halo;   // measured neutral (profiles/): off unless asked for
     op->sw_issuers2 = env_int("SINDDM_TC_ISSUERS", 2) != 1;
     op->sw_dbg = env_int("SINDDM_TC_DEBUG", 0);                 // diagnostic runs only: results are wrong when set
     // stage-granular release needs the ring to hold two whole stages plus the boxes in flight behind them
-    const int nky = p.ntaps == 9 ? 3 : 1;
+    const int nky = p.ntaps == 9 ? (op->halo ? 9 : 3) : 1;
     op->sw_stage_release = env_int("SINDDM_TC_STAGE_RELEASE", 1) != 0 && cs == 1 && op->sw_issuers2 && op->sw_peek &&
                            nst >= 2 * nky + 2;
     return SINDDM_OK;
@@ -941,6 +977,10 @@ int tc_conv_launch(const TcConvOp& op, cudaStream_t stream) {
     a.issuers2 = op.sw_issuers2;
     a.dbg = op.sw_dbg;
     a.stage_release = op.sw_stage_release;
+    a.halo = op.halo;
+    a.nsa = op.nsa;
+    a.abytes = op.abytes;
+    a.atx = op.atx;
     a.ep = p.ep;
     // algorithmic work: real pixels x N x (taps*Cin + Cres) MACs
     prof_begin(stream, 0, 2.0 * (double)p.B * p.H * p.W * p.N * ((double)p.ntaps * p.Cin + a.Cres));
