@@ -66,7 +66,7 @@ struct TcConvOp {
     int stage_bytes, nstages, smem_bytes;
     int tiles_w, tiles_h, ntiles, grid;
     int cs;   // cluster size (CTAs sharing each weight stage through TMA multicast)
-    int halo, nsa, abytes, atx;   // activation ring: one halo box per chunk for all nine taps?  slots, slot stride, box bytes
+    int halo, nh, abw, nsa, abytes, atx;   // activation ring: one halo box per chunk for all nine taps?  slots, slot stride, box bytes
     // A/B and diagnostic switches (SINDDM_TC_*), read from the environment ONCE by tc_conv_prepare
     int sw_peek, sw_l2pf, sw_issuers2, sw_dbg, sw_stage_release;
 };

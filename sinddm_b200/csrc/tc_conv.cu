@@ -58,18 +58,19 @@ constexpr int kThreads = 384;       // warp 0 TMA, warps 1-2 MMA (one per half t
 constexpr int kEpiWarp0 = 4;        // roles are warpgroup aligned so that setmaxnreg can move registers between them
 constexpr int kEpiThreads = 256;
 constexpr int kTmemCols = 512;
-constexpr int kSlots = 3;
+constexpr int kSlots = 3;        // accumulator slots rotated by two-half tiles
+constexpr int kMaxSlots = 5;     // ... by three-half tiles (narrow layers: 5 x 96 columns)
 constexpr int kStagesA = 3;   // activation (halo box) ring (halo mode: 2 slots of the larger box)
 // "halo" mode (3x3 layers): ONE (32 ch, 18 w, 18 h) box per channel chunk serves all nine taps -- tap (ky, kx) of the
 // M = 128 half tile hf (16 rows x 8 pixels) is the same box read from pixel (ky * 18 + kx + 8 * hf) on, 8-pixel core
 // groups one box row (18 x 128 B) apart: the start address moves by whole pixels (128 B), the swizzle pattern TMA wrote
 // and the tensor core reads are both functions of the absolute shared-memory address.  Activation bytes entering
 // shared memory drop 2.6x (3 x 36 KiB -> 40.5 KiB per chunk); the kernel was bound by exactly those bytes.
-constexpr int kHaloBW = kTileW + 2;                              // box width in pixels
-constexpr int kHaloPitch = kHaloBW * kKC * 4;                    // 2304 B between image rows of the box
-constexpr int kHaloBoxBytes = kBoxH * kHaloPitch;                // 41472 B
-constexpr int kHaloSlotBytes = (kHaloBoxBytes + 1023) / 1024 * 1024;
+// In halo mode the CTA tile is 16 rows x (8 * nh) pixels, nh = 2 or 3 M = 128 "halves" with one accumulator slot and
+// one MMA-issuing warp each: with nh = 3 every weight box feeds 384 pixels instead of 256 (weights are 84 % of the
+// bytes entering shared memory once the activations come as one box per chunk).
 constexpr int kHaloStagesA = 2;
+constexpr int kMaxHalves = 3;
 constexpr int kMaxStagesB = 8;   // weight box ring
 // epilogue staging: every epilogue warp owns two [32 px][16 ch] tiles (64B-swizzled, 2 KiB).  Layers that stream an
 // operand in (residual / saved pre-activation) have one result: tile 0 receives the TMA load, tile 1 is drained by
@@ -92,7 +93,10 @@ struct KernelArgs {
     uint32_t idesc;
     int issuers2;              // single-CTA kernel: warps 1 and 2 each issue the MMAs of one half tile (SINDDM_TC_ISSUERS=1: warp 1 issues both)
     int peek;                  // MMA warps test the next weight box's barrier inside the MMA asm, no per-box tcgen05 fence (SINDDM_TC_PEEK=0: off)
-    int halo;                  // one halo box per chunk for all nine taps (see kHaloBW); M halves split the tile by columns
+    int halo;                  // one halo box per chunk for all nine taps; M halves split the tile by columns
+    int nh;                    // M = 128 halves per tile (2; halo mode: 2 or 3), tile width = halo ? 8 * nh : 16 pixels
+    int nslots;                // accumulator slots the halves rotate through (3; 5 with three halves)
+    int abw;                   // halo mode: box width in pixels (8 * nh + 2)
     int nsa, abytes, atx;      // activation ring: slots, bytes between slots, bytes per box
     int stage_release;         // narrow layers (weight ring >= 2 2/3 stages): the MMA warps commit ONE barrier per stage (the
                                // halo box's empty barrier) that also releases the stage's weight boxes, instead of
@@ -106,7 +110,7 @@ struct KernelArgs {
 // smem tail (after the 1024-aligned stage ring):
 //   uint64 fullA[3], emptyA[3], fullB[8], emptyB[8], tfull[3], tempty[3], epi_in[8]; uint32 tmem_slot[4];
 //   float bias[kMaxN], wres3[kMaxN*3] (aliased by wfinal[3*kMaxN]: no layer has both), bfinal[4], fin[128*3]
-constexpr int kTailBytes = (2 * kStagesA + 2 * kMaxStagesB + 2 * kSlots + kEpiThreads / 32) * 8 + 16 +
+constexpr int kTailBytes = (2 * kStagesA + 2 * kMaxStagesB + 2 * kMaxSlots + kEpiThreads / 32) * 8 + 16 +
                            (kMaxN + kMaxN * 3 + 4 + 128 * 3) * 4 + 64;
 
 // TWO = true: CTA pairs (cluster of 2, cta_group::2): one M=256 MMA covers the same half of BOTH CTAs' tiles,
@@ -128,8 +132,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     uint64_t* fullb_bar = emptya_bar + kStagesA;
     uint64_t* emptyb_bar = fullb_bar + kMaxStagesB;
     uint64_t* tfull_bar = emptyb_bar + kMaxStagesB;
-    uint64_t* tempty_bar = tfull_bar + kSlots;
-    uint64_t* epi_in_bar = tempty_bar + kSlots;
+    uint64_t* tempty_bar = tfull_bar + kMaxSlots;
+    uint64_t* epi_in_bar = tempty_bar + kMaxSlots;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_in_bar + kEpiThreads / 32);
     float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
     float* s_wres3 = s_bias + kMaxN;
@@ -152,13 +156,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         // empty barriers: one commit per MMA-issuing warp (two in the single-CTA kernel, see below)
         for (int i = 0; i < a.nsa; ++i) {
             mbar_init(&fulla_bar[i], TWO ? 2 : 1);   // one arrival per producing CTA
-            mbar_init(&emptya_bar[i], (!TWO && a.issuers2) ? 2 : 1);
+            mbar_init(&emptya_bar[i], (!TWO && a.issuers2) ? a.nh : 1);
         }
         for (int i = 0; i < a.nstages_b; ++i) {
             mbar_init(&fullb_bar[i], TWO ? 2 : 1);
-            mbar_init(&emptyb_bar[i], (!TWO && a.issuers2) ? 2 : 1);
+            mbar_init(&emptyb_bar[i], (!TWO && a.issuers2) ? a.nh : 1);
         }
-        for (int i = 0; i < kSlots; ++i) {
+        for (int i = 0; i < kMaxSlots; ++i) {
             mbar_init(&tfull_bar[i], 1);
             mbar_init(&tempty_bar[i], (TWO ? 2 : 1) * (kEpiThreads / 32));   // one arrival per epilogue warp
         }
@@ -230,7 +234,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             const int tw = tile % a.tiles_w;
             const int th = (tile / a.tiles_w) % a.tiles_h;
             const int b = tile / (a.tiles_w * a.tiles_h);
-            const int h0 = th * kTileH, w0 = tw * kTileW;
+            const int h0 = th * kTileH, w0 = tw * (halo ? 8 * a.nh : kTileW);
             for (int it = 0; it < nst; ++it) {
                 const bool main = it < nst_main;
                 const int c = main ? it / nkx : it - nst_main;
@@ -300,7 +304,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                 }
             }
         }
-      } else if (!TWO && a.issuers2 && (warp == 1 || warp == 2)) {
+      } else if (!TWO && a.issuers2 && warp >= 1 && warp <= a.nh) {
         // ------------------------------------------------------------ MMA issuers (single-CTA kernel)
         // Issuing a tcgen05.mma costs the issuing warp ~50-70 cycles (descriptor moves into uniform registers,
         // election, predicates), which is as long as an N = 80 MMA executes: one issuing warp cannot keep the
@@ -311,17 +315,18 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         const int half = warp - 1;
         int sa_i = 0, sb_i = 0;
         uint32_t pha = 0, phb = 0;
-        uint32_t slot_uses[kSlots] = {0, 0, 0};
+        uint32_t slot_uses[kMaxSlots] = {0, 0, 0, 0, 0};
         int titer = 0;
         // high words of the operand descriptors: 8-pixel core groups are 1024 B apart (16-pixel box rows: contiguous) or,
         // in halo mode, one 18-pixel box row apart; weight boxes are dense [N][128 B]
         const uint32_t desc_hi_b = (uint32_t)(umma_smem_desc(0, 0, 1024, UMMA_LAYOUT_SW128) >> 32);
-        const uint32_t desc_hi = halo ? (uint32_t)(umma_smem_desc(0, 0, kHaloPitch, UMMA_LAYOUT_SW128) >> 32) : desc_hi_b;
+        const uint32_t desc_hi =
+            halo ? (uint32_t)(umma_smem_desc(0, 0, (uint32_t)a.abw * (kKC * 4), UMMA_LAYOUT_SW128) >> 32) : desc_hi_b;
         // byte offset of this half's operand inside the activation box for vertical tap / box index ky
         auto a_off = [&](bool main, int ky) -> uint32_t {
             if (halo) {
                 const int ty = main ? ky / 3 : 1, tx = main ? ky - 3 * (ky / 3) : 1;
-                return (uint32_t)((ty * kHaloBW + tx + 8 * half) * (kKC * 4));
+                return (uint32_t)((ty * a.abw + tx + 8 * half) * (kKC * 4));
             }
             return (uint32_t)((((main && nky == 3) ? ky : 1) + 8 * half) * kRowBytes);
         };
@@ -335,12 +340,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         bool st_ready = false;   // stage_release: the NEXT stage's (single) full barrier was seen complete by the peek
         const bool srel = a.stage_release && a.peek;
         for (int st = pair_id; st < nsuper; st += npairs, ++titer) {
-            const int s0 = (2 * titer) % kSlots, s1 = (2 * titer + 1) % kSlots;
-            const int slot = half ? s1 : s0;
-            // the slot must have been drained by the epilogue of its previous use (by either half)
+            // the nh halves of tile t use accumulator slots nh*t .. nh*t + nh-1 (mod nslots): two halves rotate through
+            // three slots, three halves through five, so a tile never waits for the epilogue of the tile before it
+            const int slot = (a.nh * titer + half) % a.nslots;
+            // the slot must have been drained by the epilogue of its previous use (by any half)
             mbar_wait(&tempty_bar[slot], (slot_uses[slot] & 1u) ^ 1u);
-            ++slot_uses[s0];
-            ++slot_uses[s1];
+            for (int hh = 0; hh < a.nh; ++hh) ++slot_uses[(a.nh * titer + hh) % a.nslots];
             tc_fence_after_sync();
             if (half == 0 && lane == 0) *reinterpret_cast<volatile uint32_t*>(&tmem_slot[1]) = (uint32_t)titer + 1u;
             const uint32_t dacc = tmem_base + (uint32_t)(slot * a.slot_stride);
@@ -554,7 +559,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         int obuf = 0;
         const float* gsrc = ep.res_add ? ep.res_add : ep.dgelu_z;   // streamed through TMA
         const float* gsrc2 = (ep.res_add && ep.dgelu_z) ? ep.dgelu_z : nullptr;   // rare second stream: plain loads
-        uint32_t slot_uses[kSlots] = {0, 0, 0};
+        uint32_t slot_uses[kMaxSlots] = {0, 0, 0, 0, 0};
         int titer = 0;
         // ep.colsum_part: column sums of everything this warp stores to `out` (its column share, its pixel quarter),
         // kept in lanes 0-15 (one column each) per chunk of the warp, written once at the end of the kernel
@@ -568,14 +573,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             const int b = tile / (a.tiles_w * a.tiles_h);
             const bool live = (tile < a.ntiles) && !(a.dbg & 2);
 #pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
-                const int slot = (2 * titer + half) % kSlots;
+            for (int half = 0; half < a.nh; ++half) {
+                const int slot = (a.nh * titer + half) % a.nslots;
                 // accumulator row -> pixel.  Stacked halves: half = 8 image rows x 16 px, this warp's strip = 2 rows x 16 px;
                 // halo mode: half = 16 rows x 8 px (columns 8*half ..), this warp's strip = 4 rows x 8 px
                 const int h = halo ? th * kTileH + (row >> 3) : th * kTileH + half * 8 + row / kTileW;
-                const int w = halo ? tw * kTileW + half * 8 + (row & 7) : tw * kTileW + row % kTileW;
+                const int w = halo ? tw * 8 * a.nh + half * 8 + (row & 7) : tw * kTileW + row % kTileW;
                 const int hq = halo ? th * kTileH + quarter * 4 : th * kTileH + half * 8 + quarter * 2;
-                const int w0 = halo ? tw * kTileW + half * 8 : tw * kTileW;   // this warp's strip
+                const int w0 = halo ? tw * 8 * a.nh + half * 8 : tw * kTileW;   // this warp's strip
                 const bool valid = live && (h < a.H) && (w < a.W);
                 const size_t pix = ((size_t)b * a.H + h) * a.W + w;
                 const unsigned vmask = ep.colsum_part ? __ballot_sync(0xffffffffu, valid) : 0u;
@@ -881,10 +886,21 @@ int tc_conv_prepare(const ConvProblem& p, TcConvOp* op) {
         const char* ei = getenv("SINDDM_TC_ISSUERS");      // the halo walk lives in the two-issuer loop
         op->halo = (p.ntaps == 9 && cs == 1 && !(e && atoi(e) == 0) && !(ei && atoi(ei) == 1)) ? 1 : 0;
     }
-    const int abw = op->halo ? kHaloBW : kTileW;       // activation box width in pixels
+    // three halves need three accumulator slots of N (rounded to 32) columns each -- always true for N <= 160
+    {
+        const char* e = getenv("SINDDM_TC_HALVES");
+        // three halves only where FIVE accumulator slots fit (N <= 96): with fewer the next tile's main loop would wait
+        // for the epilogue of this one (measured: N = 160 with three fixed slots is 20 % slower)
+        // (A/B on one box, 32x186x248: N = 80 layers -3 .. -11 %, the N = 16 data gradient -23 %; the layer whose epilogue
+        //  adds the 3-channel residual per pixel, l1.net[2], +10 % -> keeps two halves)
+        op->nh = (op->halo && !(e && atoi(e) == 2) && !p.ep.x3 &&
+                  kMaxSlots * (int)align_up((size_t)p.N, 32) <= kTmemCols) ? 3 : 2;
+    }
+    const int abw = op->halo ? 8 * op->nh + 2 : kTileW;       // activation box width in pixels
+    op->abw = abw;
     op->nsa = op->halo ? kHaloStagesA : kStagesA;
-    op->abytes = op->halo ? kHaloSlotBytes : kABytes;
-    op->atx = op->halo ? kHaloBoxBytes : kABytes;
+    op->atx = op->halo ? kBoxH * abw * kKC * 4 : kABytes;
+    op->abytes = (int)align_up((size_t)op->atx, 1024);
     SINDDM_TRY(make_tmap_nhwc(&op->tm_a, p.in, p.B, p.H, p.W, p.Cin, kKC, abw, kBoxH, CU_TENSOR_MAP_SWIZZLE_128B));
     if (p.w_blocked) memset(&op->tm_b, 0, sizeof(op->tm_b));
     else SINDDM_TRY(make_tmap_2d(&op->tm_b, p.w, p.Cin, p.ntaps * p.N, kKC, p.N / cs, CU_TENSOR_MAP_SWIZZLE_128B));
@@ -919,7 +935,7 @@ int tc_conv_prepare(const ConvProblem& p, TcConvOp* op) {
     SINDDM_REQUIRE(nst >= 3, "tc_conv: not enough shared memory for the weight ring");
     op->nstages = nst;
     op->smem_bytes = op->nsa * op->abytes + nst * op->stage_bytes + kEpiBytes + kTailBytes + 1024;
-    op->tiles_w = ceil_div(p.W, kTileW);
+    op->tiles_w = ceil_div(p.W, op->halo ? 8 * op->nh : kTileW);
     op->tiles_h = ceil_div(p.H, kTileH);
     op->ntiles = op->tiles_w * op->tiles_h * p.B;
     const int nsuper = ceil_div(op->ntiles, cs);
@@ -978,6 +994,9 @@ int tc_conv_launch(const TcConvOp& op, cudaStream_t stream) {
     a.dbg = op.sw_dbg;
     a.stage_release = op.sw_stage_release;
     a.halo = op.halo;
+    a.nh = op.nh;
+    a.nslots = op.nh == 3 ? kMaxSlots : kSlots;
+    a.abw = op.abw;
     a.nsa = op.nsa;
     a.abytes = op.abytes;
     a.atx = op.atx;
