@@ -506,7 +506,12 @@ int net_backward(Plan* pl, const float* const* params, const float* dout_nchw, f
         }
         // weight gradients of net[2] and res_conv
         SINDDM_TRY(run_wgrad(b.tc_w2, b.wg2, b.pw2, grads[b.pbase + 8], s));
-        if (b.has_res) SINDDM_TRY(run_wgrad(b.tc_wr, b.wgr, b.pwr, grads[b.pbase + 10], s));
+        if (b.has_res) {
+            if (!b.tc_wr && b.Ci == 3 && final_conv_bwd_supported(b.Co))   // l1.res_conv: one streaming pass over d_o
+                SINDDM_TRY(wgrad_from_c3_launch(b.in, d_o, P, b.Co, grads[b.pbase + 10], pl->colsum_scratch, s));
+            else
+                SINDDM_TRY(run_wgrad(b.tc_wr, b.wgr, b.pwr, grads[b.pbase + 10], s));
+        }
         // dz1 = conv3x3^T(d_o) * gelu'(z1)
         SINDDM_TRY(run_conv(b.tc_d2, b.d2, b.pd2, s));
         if (b.tc_d2 && b.pd2.ep.colsum_part)

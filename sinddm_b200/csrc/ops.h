@@ -156,6 +156,11 @@ int final_conv_bwd_launch(const float* dout_nhwc3, const float* o, const float* 
                           int round, float* dw, float* db, float* db_prev, float* db_prev2, float* scratch,
                           cudaStream_t stream);
 
+// weight gradient of a 1x1 conv FROM a 3-channel input (l1.res_conv): dw [C][3] = sum_p dy[p][c] * x3[p][j]; one read of
+// dy [P,C]; scratch as for final_conv_bwd_launch.
+int wgrad_from_c3_launch(const float* x3, const float* dy, long long P, int C, float* dw, float* scratch,
+                         cudaStream_t stream);
+
 // out[c] = sum_p a[p][c]; scratch needs colsum_scratch_floats(C) floats.
 size_t colsum_scratch_floats(int C);
 int colsum_launch(const float* a, long long P, int C, float* out, float* scratch, cudaStream_t stream);

@@ -85,6 +85,9 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, float* __rest
 constexpr int kFinalBwdBlocks = 592;   // 4 per SM
 constexpr int kFinalBwdThreads = 240;
 
+// WRITE = false: only the weight-gradient partial sums (the same reduction serves the 1x1 residual conv FROM a 3-channel
+// input, l1.res_conv: dW[c][j] = sum_p dy[p][c] * x3[p][j]).
+template <bool WRITE>
 __global__ void __launch_bounds__(kFinalBwdThreads)
 final_conv_bwd_kernel(const float* __restrict__ dout3, const float* __restrict__ o, const float* __restrict__ w,
                       float* __restrict__ d_o, long long P, int C, int round, float* __restrict__ part) {
@@ -95,7 +98,7 @@ final_conv_bwd_kernel(const float* __restrict__ dout3, const float* __restrict__
     const bool active = g < groups;
     const long long p_begin = P * blockIdx.x / gridDim.x, p_end = P * (blockIdx.x + 1) / gridDim.x;
     float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0, w2 = w0;
-    if (active) {
+    if (active && WRITE) {
         // scalar loads: parameters are views into a flat buffer, aligned to 4 bytes only
         const float* wp = w + 4 * c4;
         w0 = make_float4(__ldg(wp), __ldg(wp + 1), __ldg(wp + 2), __ldg(wp + 3));
@@ -113,6 +116,7 @@ final_conv_bwd_kernel(const float* __restrict__ dout3, const float* __restrict__
             a1.x = fmaf(d1, x.x, a1.x); a1.y = fmaf(d1, x.y, a1.y); a1.z = fmaf(d1, x.z, a1.z); a1.w = fmaf(d1, x.w, a1.w);
             a2.x = fmaf(d2, x.x, a2.x); a2.y = fmaf(d2, x.y, a2.y); a2.z = fmaf(d2, x.z, a2.z); a2.w = fmaf(d2, x.w, a2.w);
             b0 += d0; b1 += d1; b2 += d2;
+            if (!WRITE) continue;
             float4 y;
             y.x = fmaf(w2.x, d2, fmaf(w1.x, d1, w0.x * d0));
             y.y = fmaf(w2.y, d2, fmaf(w1.y, d1, w0.y * d0));
@@ -146,10 +150,11 @@ final_conv_bwd_kernel(const float* __restrict__ dout3, const float* __restrict__
 
 // dW[j][c], db[j] = fixed-order sums of the block partials; db_prev[c] = sum_j W[j][c] * db[j].  One warp per output
 // value (lanes stride over the partial rows, fixed shuffle tree); every block recomputes the three db sums it needs.
+// transpose != 0: dw is [C][3] (a conv FROM 3 channels) instead of [3][C]; db / db_prev may be null.
 __global__ void __launch_bounds__(256)
 final_conv_bwd_finish_kernel(const float* __restrict__ part, int nblk, int C, const float* __restrict__ w,
                              float* __restrict__ dw, float* __restrict__ db, float* __restrict__ db_prev,
-                             float* __restrict__ db_prev2) {
+                             float* __restrict__ db_prev2, int transpose) {
     __shared__ float sdb[3];
     const int stride = 3 * C + 4;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -162,14 +167,15 @@ final_conv_bwd_finish_kernel(const float* __restrict__ part, int nblk, int C, co
         const float s = column(3 * C + warp);
         if (lane == 0) {
             sdb[warp] = s;
-            if (blockIdx.x == 0) db[warp] = s;
+            if (blockIdx.x == 0 && db) db[warp] = s;
         }
     }
     for (int i = blockIdx.x * nwarps + warp; i < 3 * C; i += gridDim.x * nwarps) {
         const float s = column(i);
-        if (lane == 0) dw[i] = s;
+        if (lane == 0) dw[transpose ? (i % C) * 3 + i / C : i] = s;
     }
     __syncthreads();
+    if (!db_prev) return;
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
         const float v = fmaf(w[2 * C + c], sdb[2], fmaf(w[C + c], sdb[1], w[c] * sdb[0]));
         db_prev[c] = v;
@@ -215,10 +221,25 @@ int final_conv_bwd_launch(const float* dout_nhwc3, const float* o, const float* 
     const int threads = (kFinalBwdThreads / c4n) * c4n;
     int nblk = kFinalBwdBlocks;
     if ((long long)nblk > P) nblk = (int)P;
-    final_conv_bwd_kernel<<<nblk, threads, (size_t)threads * 16 * sizeof(float), stream>>>(dout_nhwc3, o, w, d_o, P, C,
-                                                                                         round, scratch);
+    final_conv_bwd_kernel<true><<<nblk, threads, (size_t)threads * 16 * sizeof(float), stream>>>(dout_nhwc3, o, w, d_o, P,
+                                                                                               C, round, scratch);
     SINDDM_CUDA_OK(cudaGetLastError());
-    final_conv_bwd_finish_kernel<<<16, 256, 0, stream>>>(scratch, nblk, C, w, dw, db, db_prev, db_prev2);
+    final_conv_bwd_finish_kernel<<<16, 256, 0, stream>>>(scratch, nblk, C, w, dw, db, db_prev, db_prev2, 0);
+    SINDDM_CUDA_OK(cudaGetLastError());
+    return SINDDM_OK;
+}
+
+int wgrad_from_c3_launch(const float* x3, const float* dy, long long P, int C, float* dw, float* scratch,
+                         cudaStream_t stream) {
+    SINDDM_REQUIRE(final_conv_bwd_supported(C), "wgrad_from_c3: C=%d unsupported", C);
+    const int c4n = C / 4;
+    const int threads = (kFinalBwdThreads / c4n) * c4n;
+    int nblk = kFinalBwdBlocks;
+    if ((long long)nblk > P) nblk = (int)P;
+    final_conv_bwd_kernel<false><<<nblk, threads, (size_t)threads * 16 * sizeof(float), stream>>>(x3, dy, nullptr, nullptr, P,
+                                                                                                C, 0, scratch);
+    SINDDM_CUDA_OK(cudaGetLastError());
+    final_conv_bwd_finish_kernel<<<16, 256, 0, stream>>>(scratch, nblk, C, nullptr, dw, nullptr, nullptr, nullptr, 1);
     SINDDM_CUDA_OK(cudaGetLastError());
     return SINDDM_OK;
 }

@@ -139,8 +139,9 @@ def test_seeded_chain_vs_reference_golden(golden, math):
         D.noise_like = lambda shape, device, repeat=False: torch.randn(shape, generator=gen).to(device)
         dif._randn = lambda shape, device: torch.randn(tuple(shape), generator=gen).to(device)
         s0 = dif.sample(batch_size=2)
-        # chains amplify per-step differences; tf32 tolerance is for 12 chained evaluations
-        atol = 5e-4 if math == "fp32" else 5e-2
+        # chains amplify per-step differences; the 246-evaluation balloons chain measures 2.7e-6 (fp32) / 2.3e-3 (tf32)
+        # max abs (tests/test_gpu_parity_r02.py): the 12-step schedule takes larger steps, bound 4x that
+        atol = 1e-4 if math == "fp32" else 1e-2
         assert (s0.cpu() - torch.from_numpy(g["chain_s0"])).abs().max() <= atol
         gen.manual_seed(6)
         s1 = dif.sample_via_scale(2, torch.from_numpy(g["chain_s0"]).to(DEV), s=1, scale_mul=(1, 1),

@@ -254,6 +254,7 @@ def test_full_sampling_chain_vs_oracle_cfg3(math):
         errs.append(float((img_p.cpu() - img_o).abs().max()))
         assert torch.isfinite(img_p).all()
     print(f"cfg-3 chain {math}: max abs error per scale {['%.2e' % e for e in errs]} on values in [-1, 1]")
-    # measured (r02): fp32 <= 3e-5 ..., tf32 <= ...; bounds = 2x measured, see DESIGN.md section 3
-    bound = 1e-3 if math == "fp32" else 5e-2
+    # measured (r02, B200): fp32 <= 2.7e-6, tf32 <= 2.3e-3 max abs on values in [-1, 1]; bounds ~ 2x measured (tf32) and
+    # 4x (fp32: a handful of ulps after 246 chained evaluations)
+    bound = 1e-5 if math == "fp32" else 5e-3
     assert max(errs) <= bound, errs

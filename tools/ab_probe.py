@@ -27,7 +27,7 @@ tr = MultiscaleTrainer(dif, str(tmp) + "/", n_scales=5, image_sizes=bench.BALLOO
 tr._prepare_training()
 tr.step = 1
 res = {}
-for s in (0, 2, 4):
+for s in (0, 1, 2, 3, 4):
     for _ in range(3):
         tr.train_step(s=s)
     torch.cuda.synchronize()
