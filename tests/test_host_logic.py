@@ -223,3 +223,99 @@ def test_flattened_parameters_keep_the_module_surface():
         off += p.numel()
     flat.add_(1.0)                                    # a kernel writing the flat vector updates every parameter
     assert all(torch.equal(net.state_dict()[k], before[k] + 1.0) for k in before)
+
+
+# ---- image2image helpers: known answers and an independent restatement ------------------------
+
+def test_dilate_mask_known_answers_and_bruteforce_restatement():
+    """functions.py:21-33 = skimage.morphology.binary_dilation(disk(r)) -> skimage.filters.gaussian(sigma=5) ->
+    min-max normalisation.  skimage is absent here, so the scipy-based product code is pinned by
+      (1) the disk footprint's known lattice-point counts (Gauss circle problem: N(7) = 149, N(20) = 1257),
+      (2) a brute-force restatement written from the definitions (OR over footprint shifts; separable Gaussian with
+          radius int(4 * sigma + 0.5), weights exp(-x^2 / (2 sigma^2)) normalised, edge replication), and
+      (3) symmetry / range properties."""
+    import torch
+    from sinddm_b200.functions import _disk, dilate_mask
+    assert int(_disk(7).sum()) == 149 and int(_disk(20).sum()) == 1257
+    assert _disk(7).shape == (15, 15) and _disk(7)[0, 7] and not _disk(7)[0, 6]
+
+    H, W = 45, 61
+    mask = np.zeros((3, H, W), np.float32)
+    mask[0, 22, 30] = 1.0                 # a single pixel ...
+    mask[0, 5:8, 50:58] = 0.3             # ... and a block near the border (any non-zero value is foreground)
+    got = dilate_mask(torch.from_numpy(mask), mode="harmonization")
+    assert got.shape == (1, 1, H, W) and got.dtype == np.float64
+
+    # brute force
+    fg = mask[0] != 0
+    dil = np.zeros((H, W), bool)
+    for y in range(H):
+        for x in range(W):
+            if fg[y, x]:
+                for dy in range(-7, 8):
+                    for dx in range(-7, 8):
+                        if dy * dy + dx * dx <= 49 and 0 <= y + dy < H and 0 <= x + dx < W:
+                            dil[y + dy, x + dx] = True
+    assert int(dil[15:30, 23:38].sum()) == 149                                  # the single pixel became the disk
+    r = int(4.0 * 5 + 0.5)
+    k = np.exp(-0.5 * (np.arange(-r, r + 1) / 5.0) ** 2)
+    k /= k.sum()
+    img = dil.astype(np.float64)
+    tmp = np.zeros_like(img)
+    for y in range(H):                                                           # rows, then columns; edge replication
+        for x in range(W):
+            tmp[y, x] = sum(k[j + r] * img[y, min(max(x + j, 0), W - 1)] for j in range(-r, r + 1))
+    out = np.zeros_like(img)
+    for y in range(H):
+        for x in range(W):
+            out[y, x] = sum(k[j + r] * tmp[min(max(y + j, 0), H - 1), x] for j in range(-r, r + 1))
+    want = (out - out.min()) / (out.max() - out.min())
+    np.testing.assert_allclose(got[0, 0], want, rtol=0, atol=1e-12)
+    assert got.min() == 0.0 and got.max() == 1.0
+
+    # an isolated pixel gives a result symmetric under the square's symmetries
+    m2 = np.zeros((1, 41, 41), np.float32)
+    m2[0, 20, 20] = 1
+    g2 = dilate_mask(torch.from_numpy(m2), mode="editing")[0, 0]
+    np.testing.assert_allclose(g2, g2[::-1, :], atol=1e-14)
+    np.testing.assert_allclose(g2, g2.T, atol=1e-14)
+    assert g2[20, 20] == 1.0
+    with pytest.raises(ValueError):
+        dilate_mask(torch.from_numpy(m2), mode="nope")
+
+
+def test_match_histograms_known_answers():
+    """skimage.exposure.match_histograms 0.19 (trainer.py:313 calls it with channel_axis=2): every source value maps to
+    the reference value of the same quantile, np.interp between reference quantiles, result cast to the input dtype.
+    Hand-derived cases."""
+    from sinddm_b200.functions import match_histograms
+    # one-to-one quantiles
+    src = np.array([[0, 1], [2, 3]], np.uint8)
+    ref = np.array([[10, 20], [30, 40]], np.uint8)
+    np.testing.assert_array_equal(match_histograms(src, ref), ref)
+    # ties: source quantiles .5, .75, 1.0 against reference quantiles .25, .5, .75, 1.0
+    np.testing.assert_array_equal(match_histograms(np.array([0, 0, 1, 2], np.uint8), np.array([10, 20, 30, 40], np.uint8)),
+                                  [20, 20, 30, 40])
+    # interpolation: reference {0, 10} has quantiles .5 and 1.0; source quantiles .25 .5 .75 1.0 (exact in binary)
+    np.testing.assert_array_equal(match_histograms(np.arange(4, dtype=np.uint8), np.array([0, 10], np.uint8)),
+                                  [0, 0, 5, 10])
+    # truncation to the input dtype (not rounding): reference {0, 3}: .75 -> 1.5 -> 1
+    np.testing.assert_array_equal(match_histograms(np.arange(4, dtype=np.uint8), np.array([0, 3], np.uint8)),
+                                  [0, 0, 1, 3])
+    # float images keep float values
+    out = match_histograms(np.array([0.0, 1.0, 2.0, 3.0]), np.array([0.0, 3.0]))
+    np.testing.assert_allclose(out, [0.0, 0.0, 1.5, 3.0])
+    # an image matched to itself is unchanged; per-channel matching treats channels independently
+    rs = np.random.RandomState(0)
+    img = rs.randint(0, 256, (17, 13, 3)).astype(np.uint8)
+    np.testing.assert_array_equal(match_histograms(img, img, channel_axis=2), img)
+    ref3 = rs.randint(0, 256, (9, 11, 3)).astype(np.uint8)
+    m = match_histograms(img, ref3, channel_axis=2)
+    for c in range(3):
+        np.testing.assert_array_equal(m[..., c], match_histograms(img[..., c], ref3[..., c]))
+        # matched values never leave the reference channel's range, order of pixels is preserved
+        assert m[..., c].min() >= ref3[..., c].min() and m[..., c].max() <= ref3[..., c].max()
+        o = np.argsort(img[..., c].reshape(-1), kind="stable")
+        assert np.all(np.diff(m[..., c].reshape(-1)[o].astype(int)) >= 0)
+    with pytest.raises(ValueError):
+        match_histograms(img, ref3[..., :2], channel_axis=2)
