@@ -139,6 +139,15 @@ SINDDM_DEVINL bool elect_one_sync() {
     return pred != 0;
 }
 
+// Programmatic dependent launch (host_common.h: launch_pdl): wait until the previous kernel of the stream has completed
+// and its memory is visible, then let the NEXT kernel's CTAs start as soon as this grid's CTAs retire.  Must precede the
+// kernel's first global-memory access; everything before it (barrier init, TMEM allocation, descriptor prefetch, index
+// arithmetic) overlaps the predecessor's tail.  A no-op when the kernel was launched without the attribute.
+SINDDM_DEVINL void pdl_grid_sync() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 SINDDM_DEVINL float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

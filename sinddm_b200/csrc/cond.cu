@@ -17,6 +17,7 @@ constexpr int HD = 4 * kTimeDim;  // 128 hidden of time_mlp
 __global__ void __launch_bounds__(128)
 cond_fwd_kernel(const CondParams P, const long long* __restrict__ time, float scale, const float* __restrict__ freqs,
                 int B, CondSaved S, float* __restrict__ cond) {
+    pdl_grid_sync();   // programmatic dependent launch: nothing above touches global memory
     __shared__ float emb[ED], g1[HD], g2[TD], m[TD];
     const int b = blockIdx.x, t = threadIdx.x;
 
@@ -79,6 +80,7 @@ __global__ void __launch_bounds__(128)
 cond_bwd_chain_kernel(const CondParams P, int B, CondSaved S, const float* __restrict__ dcond,
                       float* __restrict__ dm /*[4][B][32]*/, float* __restrict__ dcv /*[B][32]*/,
                       float* __restrict__ dh1 /*[B][128]*/) {
+    pdl_grid_sync();   // programmatic dependent launch: nothing above touches global memory
     __shared__ float s_dm[TD], s_dg2[TD], s_dcv[TD];
     const int b = blockIdx.x, t = threadIdx.x;
     if (t < TD) s_dg2[t] = 0.f;
@@ -128,6 +130,7 @@ struct OuterJobs {
 };
 
 __global__ void cond_bwd_weights_kernel(const OuterJobs jobs, int B) {
+    pdl_grid_sync();   // programmatic dependent launch: nothing above touches global memory
     const OuterJob J = jobs.j[blockIdx.y];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= J.rows * (J.cols + 1)) return;
@@ -162,7 +165,7 @@ CondSaved cond_saved_carve(float* base, int B) {
 
 int cond_fwd_launch(const CondParams& P, const long long* time, float scale, const float* freqs, int B,
                     const CondSaved& S, float* cond, cudaStream_t stream) {
-    cond_fwd_kernel<<<B, 128, 0, stream>>>(P, time, scale, freqs, B, S, cond);
+    (void)launch_pdl(cond_fwd_kernel, dim3(B), dim3(128), (size_t)(0), stream, P, time, scale, freqs, B, S, cond);
     SINDDM_CUDA_OK(cudaGetLastError());
     return SINDDM_OK;
 }
@@ -172,7 +175,7 @@ int cond_bwd_launch(const CondParams& P, const CondGrads& G, int B, const CondSa
     float* dm = scratch;
     float* dcv = dm + (size_t)kNumBlocks * B * TD;
     float* dh1 = dcv + (size_t)B * TD;
-    cond_bwd_chain_kernel<<<B, 128, 0, stream>>>(P, B, S, dcond, dm, dcv, dh1);
+    (void)launch_pdl(cond_bwd_chain_kernel, dim3(B), dim3(128), (size_t)(0), stream, P, B, S, dcond, dm, dcv, dh1);
     SINDDM_CUDA_OK(cudaGetLastError());
 
     OuterJobs jobs;
@@ -191,7 +194,7 @@ int cond_bwd_launch(const CondParams& P, const CondGrads& G, int B, const CondSa
         coff += (size_t)B * P.C[l];
     }
     dim3 grid(ceil_div(maxel, 128), 2 + 2 * kNumBlocks);
-    cond_bwd_weights_kernel<<<grid, 128, 0, stream>>>(jobs, B);
+    (void)launch_pdl(cond_bwd_weights_kernel, dim3(grid), dim3(128), (size_t)(0), stream, jobs, B);
     SINDDM_CUDA_OK(cudaGetLastError());
     return SINDDM_OK;
 }

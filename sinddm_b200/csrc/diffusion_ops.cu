@@ -25,6 +25,7 @@ __global__ void qsample_mix_kernel(const float* __restrict__ x_start, const floa
                                    const float* __restrict__ sqrt_ac, const float* __restrict__ sqrt_1mac,
                                    const float* __restrict__ gammas, float* __restrict__ out, int B,
                                    long long per_sample) {
+    pdl_grid_sync();   // programmatic dependent launch: nothing above touches global memory
     const long long total = (long long)B * per_sample;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -45,6 +46,7 @@ constexpr int kLossBlocks = 296;
 __global__ void __launch_bounds__(256)
 l1_partial_kernel(const float* __restrict__ noise, const float* __restrict__ pred, long long n, float inv_n,
                   float* __restrict__ partial, float* __restrict__ dpred) {
+    pdl_grid_sync();   // programmatic dependent launch: nothing above touches global memory
     __shared__ float wsum[8];
     float s = 0.f;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -65,6 +67,7 @@ l1_partial_kernel(const float* __restrict__ noise, const float* __restrict__ pre
 }
 
 __global__ void l1_final_kernel(const float* __restrict__ partial, int nblk, float inv_n, float* __restrict__ loss) {
+    pdl_grid_sync();   // programmatic dependent launch: nothing above touches global memory
     __shared__ float wsum[32];
     float s = 0.f;
     for (int i = threadIdx.x; i < nblk; i += blockDim.x) s += partial[i];
@@ -79,6 +82,7 @@ __global__ void l1_final_kernel(const float* __restrict__ partial, int nblk, flo
 }
 
 __global__ void ddpm_step_kernel(const DdpmStepArgs a) {
+    pdl_grid_sync();   // programmatic dependent launch: nothing above touches global memory
     const long long total = (long long)a.B * a.per_sample;
     const bool reblur = a.reblur_mode != 0;
     const bool t0_pos = a.t[0] > 0;  // the reference branches on t[0] (models.py:331,434)
@@ -142,7 +146,7 @@ int qsample_mix_launch(const float* x_start, const float* x_orig, const float* n
                        long long per_sample, cudaStream_t stream) {
     SINDDM_REQUIRE(gammas == nullptr || x_orig != nullptr, "qsample_mix: gammas given without x_orig");
     const long long total = (long long)B * per_sample;
-    qsample_mix_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x_start, x_orig, noise, t, sqrt_ac, sqrt_1mac, gammas,
+    (void)launch_pdl(qsample_mix_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), stream, x_start, x_orig, noise, t, sqrt_ac, sqrt_1mac, gammas,
                                                                  out, B, per_sample);
     SINDDM_CUDA_OK(cudaGetLastError());
     return SINDDM_OK;
@@ -156,9 +160,9 @@ int l1_loss_launch(const float* noise, const float* pred, long long n, float* lo
     const float inv_n = 1.0f / (float)n;
     int nblk = grid_for(n, 256);
     if (nblk > kLossBlocks) nblk = kLossBlocks;
-    l1_partial_kernel<<<nblk, 256, 0, stream>>>(noise, pred, n, inv_n, scratch, dpred);
+    (void)launch_pdl(l1_partial_kernel, dim3(nblk), dim3(256), (size_t)(0), stream, noise, pred, n, inv_n, scratch, dpred);
     SINDDM_CUDA_OK(cudaGetLastError());
-    l1_final_kernel<<<1, 256, 0, stream>>>(scratch, nblk, inv_n, loss);
+    (void)launch_pdl(l1_final_kernel, dim3(1), dim3(256), (size_t)(0), stream, scratch, nblk, inv_n, loss);
     SINDDM_CUDA_OK(cudaGetLastError());
     return SINDDM_OK;
 }
@@ -166,7 +170,7 @@ int l1_loss_launch(const float* noise, const float* pred, long long n, float* lo
 int ddpm_step_launch(const DdpmStepArgs& a, cudaStream_t stream) {
     SINDDM_REQUIRE(!a.reblur_mode || (a.x_tilde && a.gammas), "ddpm_step: re-blur mode needs x_tilde and gammas");
     const long long total = (long long)a.B * a.per_sample;
-    ddpm_step_kernel<<<grid_for(total, 256), 256, 0, stream>>>(a);
+    (void)launch_pdl(ddpm_step_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), stream, a);
     SINDDM_CUDA_OK(cudaGetLastError());
     return SINDDM_OK;
 }

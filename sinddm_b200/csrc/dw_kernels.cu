@@ -159,6 +159,7 @@ dw5x5_wgrad_partial_kernel(const float* __restrict__ x, const float* __restrict_
 // stage 2: dcond[b][c] = sum_chunk s[b][chunk][25][c]; dw[c][tap] = sum_b sum_chunk s[..][tap][c]; db = sum_b dcond
 __global__ void dw5x5_wgrad_final_kernel(const float* __restrict__ scratch, float* __restrict__ dw,
                                          float* __restrict__ db, float* __restrict__ dcond, int B, int C, int nchunk) {
+    pdl_grid_sync();   // programmatic dependent launch: nothing above touches global memory
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const int i = blockIdx.y;  // 0..25
@@ -186,6 +187,7 @@ __global__ void __launch_bounds__(256)
 dw5x5_c3_kernel(const float* __restrict__ in, const float* __restrict__ wgt, const float* __restrict__ bias,
                 const float* __restrict__ cond, const float* __restrict__ add, float* __restrict__ out, int B, int H,
                 int W, int flip, int round) {
+    pdl_grid_sync();   // programmatic dependent launch: nothing above touches global memory
     float wr[25][3];
 #pragma unroll
     for (int t = 0; t < 25; ++t)
@@ -224,6 +226,7 @@ dw5x5_c3_kernel(const float* __restrict__ in, const float* __restrict__ wgt, con
 __global__ void __launch_bounds__(256)
 dw5x5_wgrad_c3_kernel(const float* __restrict__ x, const float* __restrict__ dh, float* __restrict__ scratch, int H,
                       int W, int nchunk) {
+    pdl_grid_sync();   // programmatic dependent launch: nothing above touches global memory
     __shared__ float red[8][78];
     const int b = blockIdx.y, chunk = blockIdx.x;
     const int HW = H * W;
@@ -375,6 +378,7 @@ dw5x5_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const float* __restr
         mbar_init(&bar[1], 1);
         fence_mbar_init();
     }
+    pdl_grid_sync();
     __syncthreads();
     if (tid == 0) {
         mbar_arrive_expect_tx(&bar[0], kTileFloats * sizeof(float));
@@ -437,6 +441,7 @@ dw5x5_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const float* __restr
 // out[c] = sum_k part[k][C]: block = 32 channels x 8 partial-sum lanes
 __global__ void __launch_bounds__(256) csum_final_kernel(const float* __restrict__ part, int nparts, int C,
                                                          float* __restrict__ out, float* __restrict__ out2) {
+    pdl_grid_sync();   // programmatic dependent launch: nothing above touches global memory
     __shared__ float red[8][32];
     const int c = blockIdx.x * 32 + threadIdx.x;
     float t = 0.f;
@@ -479,6 +484,7 @@ dw5x5_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __
         mbar_init(&bar[1], 1);
         fence_mbar_init();
     }
+    pdl_grid_sync();
     __syncthreads();
     if (tid == 0) {
         mbar_arrive_expect_tx(&bar[0], kTileFloats * sizeof(float));
@@ -571,12 +577,12 @@ static int dw5x5_tma_launch(const CUtensorMap& tm, const float* w, const float* 
     const int tpc = tiles_per_cta(tiles_w, (long long)ncg * tiles_h * B, kMaxTilesPerCta);
     dim3 grid(ncg * ceil_div(tiles_w, tpc), tiles_h, B);
     dim3 block(32, kRowThreads);
-    dw5x5_tma_kernel<ADD, ROUND, CSUM><<<grid, block, smem, stream>>>(tm, w, bias, cond, add, out, H, W, C, tiles_w,
-                                                                       ncg, tpc, flip, csum_scratch);
+    (void)launch_pdl(dw5x5_tma_kernel<ADD, ROUND, CSUM>, grid, block, (size_t)smem, stream, tm, w, bias, cond, add, out, H, W,
+                     C, tiles_w, ncg, tpc, flip, csum_scratch);
     SINDDM_CUDA_OK(cudaGetLastError());
     if (CSUM) {
         const int nparts = (int)(grid.x / ncg) * tiles_h * B;
-        csum_final_kernel<<<ncg, dim3(32, 8), 0, stream>>>(csum_scratch, nparts, C, csum_out, csum_out2);
+        (void)launch_pdl(csum_final_kernel, dim3(ncg), dim3(dim3(32, 8)), (size_t)(0), stream, csum_scratch, nparts, C, csum_out, csum_out2);
         SINDDM_CUDA_OK(cudaGetLastError());
     }
     return SINDDM_OK;
@@ -628,7 +634,7 @@ int dw5x5_launch(const float* in, const float* w, const float* bias, const float
         const long long P = (long long)B * H * W;
         const long long cap = 8ll * (device_info().initialized ? device_info().num_sms : 148);
         const long long want = (P + 255) / 256;
-        dw5x5_c3_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, stream>>>(in, w, bias, cond, add, out, B, H, W,
+        (void)launch_pdl(dw5x5_c3_kernel, dim3((unsigned)(want < cap ? want : cap)), dim3(256), (size_t)(0), stream, in, w, bias, cond, add, out, B, H, W,
                                                                                  flip, round_tf32);
         SINDDM_CUDA_OK(cudaGetLastError());
         return SINDDM_OK;
@@ -670,11 +676,12 @@ int dw5x5_wgrad_launch(const float* x, const float* dh, float* dw, float* db, fl
         nchunk = tiles_h * nseg;
         dim3 grid(ncg * nseg, tiles_h, B);
         dim3 block(32, kRowThreads);
-        dw5x5_wgrad_tma_kernel<<<grid, block, smem, stream>>>(tm, dh, scratch, H, W, C, tiles_w, ncg, tpc, nseg);
+        (void)launch_pdl(dw5x5_wgrad_tma_kernel, grid, block, (size_t)smem, stream, tm, dh, scratch, H, W, C, tiles_w, ncg, tpc,
+                         nseg);
     } else if (C == 3) {
         nchunk = ceil_div(H, kRowsPerChunk);
         if (nchunk > 16) nchunk = 16;
-        dw5x5_wgrad_c3_kernel<<<dim3(nchunk, B), 256, 0, stream>>>(x, dh, scratch, H, W, nchunk);
+        (void)launch_pdl(dw5x5_wgrad_c3_kernel, dim3(dim3(nchunk, B)), dim3(256), (size_t)(0), stream, x, dh, scratch, H, W, nchunk);
     } else {
         nchunk = ceil_div(H, kRowsPerChunk);
         dim3 grid(ceil_div(C, 32), nchunk, B);
@@ -683,7 +690,7 @@ int dw5x5_wgrad_launch(const float* x, const float* dh, float* dw, float* db, fl
     }
     SINDDM_CUDA_OK(cudaGetLastError());
     dim3 grid2(ceil_div(C, 64), 26);
-    dw5x5_wgrad_final_kernel<<<grid2, 64, 0, stream>>>(scratch, dw, db, dcond, B, C, nchunk);
+    (void)launch_pdl(dw5x5_wgrad_final_kernel, dim3(grid2), dim3(64), (size_t)(0), stream, scratch, dw, db, dcond, B, C, nchunk);
     SINDDM_CUDA_OK(cudaGetLastError());
     return SINDDM_OK;
 }

@@ -59,6 +59,7 @@ SINDDM_DEVINL void adam_one(float g, float& p, float& m, float& v, const FusedSt
 }
 
 __global__ void __launch_bounds__(256) fused_allreduce_adam_ema_kernel(const Args a) {
+    pdl_grid_sync();   // programmatic dependent launch: nothing above touches global memory
     const FusedStepDesc& d = a.d;
     const int world = d.world, rank = d.rank;
     if (world > 1) {
@@ -138,7 +139,7 @@ int fused_step_launch(const FusedStepDesc& d, cudaStream_t stream) {
     const int sms = device_info().initialized ? device_info().num_sms : 148;
     long long want = (d.n / 4 + 255) / 256;
     const int grid = (int)(want < sms ? want : sms);
-    fused_allreduce_adam_ema_kernel<<<grid, 256, 0, stream>>>(a);
+    (void)launch_pdl(fused_allreduce_adam_ema_kernel, dim3(grid), dim3(256), (size_t)(0), stream, a);
     SINDDM_CUDA_OK(cudaGetLastError());
     return SINDDM_OK;
 }

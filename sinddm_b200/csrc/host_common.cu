@@ -1,6 +1,8 @@
 // Error slot, device init and TMA descriptor encoding.
 #include "host_common.h"
 
+#include <stdlib.h>
+
 #include <cudaTypedefs.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -20,6 +22,25 @@ void set_error(const char* fmt, ...) {
 const char* last_error() { return g_err; }
 
 static unsigned long long g_launches = 0;
+
+namespace {
+bool g_pdl_call = false;   // off outside the network driver's small-problem scopes
+}
+bool pdl_enabled() {
+    static const bool on = []() {
+        const char* e = getenv("SINDDM_PDL");
+        return !(e && atoi(e) == 0);
+    }();
+    return on && g_pdl_call;
+}
+void pdl_set(bool on) { g_pdl_call = on; }
+long long pdl_max_pixels() {
+    static const long long v = []() {
+        const char* e = getenv("SINDDM_PDL_MAX_PX");
+        return e ? atoll(e) : 400000ll;
+    }();
+    return v;
+}
 
 void note_call(const char* expr) {
     // "cudaGetLastError()" is what follows every <<<>>> launch in this library

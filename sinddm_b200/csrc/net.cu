@@ -12,6 +12,8 @@
 // (Cin >= 8 and N % 16 == 0); the 3-channel layers and math == MATH_FP32 use the CUDA-core twin.
 #include "net.h"
 
+#include "common.cuh"
+
 #include <stdlib.h>
 #include <string.h>
 
@@ -378,12 +380,17 @@ int plan_build(Plan* pl, int B, int H, int W, int dim, int channels, int math, i
 
 __global__ void add_vec_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o,
                                int n) {
+    pdl_grid_sync();   // programmatic dependent launch: nothing above touches global memory
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) o[i] = a[i] + b[i];
 }
 
 int net_pack_weights(Plan* pl, const float* const* params, cudaStream_t s) {
     const int rnd = pl->math == MATH_TF32 ? 1 : 0;
+    struct PdlScope {
+        explicit PdlScope(long long px) { pdl_set(px <= pdl_max_pixels()); }
+        ~PdlScope() { pdl_set(false); }
+    } pdl_scope(pl->P);
     for (int l = 0; l < kNumBlocks; ++l) {
         BlockBufs& b = pl->blk[l];
         // tensor-core layers read the blocked pre-swizzled layout, CUDA-core layers the plain [tap][N][K] one
@@ -409,7 +416,7 @@ int net_pack_weights(Plan* pl, const float* const* params, cudaStream_t s) {
                 SINDDM_TRY(pack_conv_weights_launch(params[b.pbase + 10], b.Co, b.Ci, 1, b.wr_f, b.wr_d,
                                                     rnd && b.tc_c2, s, b.tc_c2 && pl->blocked_weights));
             // net[2].bias + res_conv.bias enter the same epilogue
-            add_vec_kernel<<<ceil_div(b.Co, 128), 128, 0, s>>>(params[b.pbase + 9], params[b.pbase + 11], b.bias2c,
+            (void)launch_pdl(add_vec_kernel, dim3(ceil_div(b.Co, 128)), dim3(128), (size_t)(0), s, params[b.pbase + 9], params[b.pbase + 11], b.bias2c,
                                                               b.Co);
             SINDDM_CUDA_OK(cudaGetLastError());
         }
@@ -441,6 +448,10 @@ int net_forward(Plan* pl, const float* const* params, const float* x_nchw, const
                 const float* freqs, float* out_nchw, cudaStream_t s) {
     const int B = pl->B, H = pl->H, W = pl->W;
     const int rnd = pl->math == MATH_TF32 ? 1 : 0;
+    struct PdlScope {   // programmatic dependent launches only where the launch overheads matter (small problems)
+        explicit PdlScope(long long px) { pdl_set(px <= pdl_max_pixels()); }
+        ~PdlScope() { pdl_set(false); }
+    } pdl_scope(pl->P);
     SINDDM_TRY(nchw_to_nhwc_launch(x_nchw, pl->x_nhwc, B, pl->channels, H, W, s));
     CondParams cp;
     fill_cond_params(pl, params, &cp);
@@ -474,6 +485,10 @@ int net_backward(Plan* pl, const float* const* params, const float* dout_nchw, f
     const int B = pl->B, H = pl->H, W = pl->W;
     const long long P = pl->P;
     const int rnd = pl->math == MATH_TF32 ? 1 : 0;
+    struct PdlScope {
+        explicit PdlScope(long long px) { pdl_set(px <= pdl_max_pixels()); }
+        ~PdlScope() { pdl_set(false); }
+    } pdl_scope(P);
 
     // ---- final_conv: bias / weight gradients and the gradient into l4's output
     SINDDM_TRY(nchw_to_nhwc_launch(dout_nchw, pl->dout_nhwc, B, pl->channels, H, W, s));

@@ -183,6 +183,7 @@ __global__ void simt_wgrad_kernel(const WgradProblem p) {
 // dst[co][ci][tap] (or [tap][ci][co] when keep_layout) = sum_s partial[s][tap][ci][co], fixed order.
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int nsplit, int ntaps, int Cx, int Cy,
                                     float* __restrict__ dst, int keep_layout) {
+    pdl_grid_sync();   // programmatic dependent launch: nothing above touches global memory
     const int total = ntaps * Cx * Cy;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
@@ -225,6 +226,7 @@ __device__ __forceinline__ size_t packed_index(int tap, int n, int k, int N, int
 __global__ void pack_conv_weights_kernel(const float* __restrict__ w, int Cout, int Cin, int ntaps,
                                          float* __restrict__ dst_fwd, float* __restrict__ dst_dgrad, int round,
                                          int blocked, int dgrad_rows) {
+    pdl_grid_sync();   // programmatic dependent launch: nothing above touches global memory
     const int total = Cout * Cin * ntaps;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
@@ -245,6 +247,7 @@ __global__ void pack_conv_weights_kernel(const float* __restrict__ w, int Cout, 
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 im2col3x3_c3_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int H, int W, int round) {
+    pdl_grid_sync();   // programmatic dependent launch: nothing above touches global memory
     const long long total = (long long)B * H * W * 8;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int q = (int)(i & 7);
@@ -268,6 +271,7 @@ im2col3x3_c3_kernel(const float* __restrict__ x, float* __restrict__ out, int B,
 // w [Co][3][3][3] (OIHW) -> the 1x1 GEMM operand [1][Co][32] with k = tap*3 + c, in either packed layout
 __global__ void pack_im2col_weights_kernel(const float* __restrict__ w, int Co, float* __restrict__ dst, int round,
                                            int blocked) {
+    pdl_grid_sync();   // programmatic dependent launch: nothing above touches global memory
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Co * 27) return;
     const int tap = i % 9, c = (i / 9) % 3, co = i / 27;
@@ -799,7 +803,7 @@ int simt_wgrad_launch(const WgradProblem& p, cudaStream_t stream) {
 int wgrad_reduce_launch(const float* partial, int nsplit, int ntaps, int Cx, int Cy, float* dst, int keep_layout,
                         cudaStream_t stream) {
     const int total = ntaps * Cx * Cy;
-    wgrad_reduce_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(partial, nsplit, ntaps, Cx, Cy, dst, keep_layout);
+    (void)launch_pdl(wgrad_reduce_kernel, dim3(ceil_div(total, 256)), dim3(256), (size_t)(0), stream, partial, nsplit, ntaps, Cx, Cy, dst, keep_layout);
     SINDDM_CUDA_OK(cudaGetLastError());
     return SINDDM_OK;
 }
@@ -808,13 +812,13 @@ int im2col3x3_c3_launch(const float* x, float* out, int B, int H, int W, int rou
     const long long total = (long long)B * H * W * 8;
     const long long cap = 16ll * (device_info().initialized ? device_info().num_sms : 148);
     const long long want = (total + 255) / 256;
-    im2col3x3_c3_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, stream>>>(x, out, B, H, W, round);
+    (void)launch_pdl(im2col3x3_c3_kernel, dim3((unsigned)(want < cap ? want : cap)), dim3(256), (size_t)(0), stream, x, out, B, H, W, round);
     SINDDM_CUDA_OK(cudaGetLastError());
     return SINDDM_OK;
 }
 
 int pack_im2col_weights_launch(const float* w, int Co, float* dst, int round, int blocked, cudaStream_t stream) {
-    pack_im2col_weights_kernel<<<ceil_div(Co * 27, 256), 256, 0, stream>>>(w, Co, dst, round, blocked);
+    (void)launch_pdl(pack_im2col_weights_kernel, dim3(ceil_div(Co * 27, 256)), dim3(256), (size_t)(0), stream, w, Co, dst, round, blocked);
     SINDDM_CUDA_OK(cudaGetLastError());
     return SINDDM_OK;
 }
@@ -822,7 +826,7 @@ int pack_im2col_weights_launch(const float* w, int Co, float* dst, int round, in
 int pack_conv_weights_launch(const float* w, int Cout, int Cin, int ntaps, float* dst_fwd, float* dst_dgrad, int round,
                              cudaStream_t stream, int blocked, int dgrad_rows) {
     const int total = Cout * Cin * ntaps;
-    pack_conv_weights_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(w, Cout, Cin, ntaps, dst_fwd, dst_dgrad, round,
+    (void)launch_pdl(pack_conv_weights_kernel, dim3(ceil_div(total, 256)), dim3(256), (size_t)(0), stream, w, Cout, Cin, ntaps, dst_fwd, dst_dgrad, round,
                                                                        blocked, dgrad_rows > Cin ? dgrad_rows : Cin);
     SINDDM_CUDA_OK(cudaGetLastError());
     return SINDDM_OK;

@@ -35,6 +35,7 @@ __global__ void colsum_partial_kernel(const float* __restrict__ a, long long P, 
 // block = 32 channels x 8 lanes over the partial sums (fixed order: deterministic)
 __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ scratch, int nblk, int C,
                                                            float* __restrict__ out) {
+    pdl_grid_sync();   // programmatic dependent launch: nothing above touches global memory
     __shared__ float red[8][32];
     const int c = blockIdx.x * 32 + threadIdx.x;
     float s = 0.f;
@@ -51,6 +52,7 @@ __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restri
 }
 
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int C, int HW) {
+    pdl_grid_sync();   // programmatic dependent launch: nothing above touches global memory
     const long long total = (long long)B * C * HW;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -91,6 +93,7 @@ template <bool WRITE>
 __global__ void __launch_bounds__(kFinalBwdThreads)
 final_conv_bwd_kernel(const float* __restrict__ dout3, const float* __restrict__ o, const float* __restrict__ w,
                       float* __restrict__ d_o, long long P, int C, int round, float* __restrict__ part) {
+    pdl_grid_sync();   // programmatic dependent launch: nothing above touches global memory
     extern __shared__ float red[];   // [groups][16]
     const int c4n = C >> 2;                                   // threads per pixel
     const int groups = blockDim.x / c4n;
@@ -155,6 +158,7 @@ __global__ void __launch_bounds__(256)
 final_conv_bwd_finish_kernel(const float* __restrict__ part, int nblk, int C, const float* __restrict__ w,
                              float* __restrict__ dw, float* __restrict__ db, float* __restrict__ db_prev,
                              float* __restrict__ db_prev2, int transpose) {
+    pdl_grid_sync();   // programmatic dependent launch: nothing above touches global memory
     __shared__ float sdb[3];
     const int stride = 3 * C + 4;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -204,7 +208,7 @@ int colsum_launch(const float* a, long long P, int C, float* out, float* scratch
     dim3 block(C, lanes);
     colsum_partial_kernel<<<nblk, block, (size_t)lanes * C * sizeof(float), stream>>>(a, P, C, scratch);
     SINDDM_CUDA_OK(cudaGetLastError());
-    colsum_final_kernel<<<ceil_div(C, 32), dim3(32, 8), 0, stream>>>(scratch, nblk, C, out);
+    (void)launch_pdl(colsum_final_kernel, dim3(ceil_div(C, 32)), dim3(dim3(32, 8)), (size_t)(0), stream, scratch, nblk, C, out);
     SINDDM_CUDA_OK(cudaGetLastError());
     return SINDDM_OK;
 }
@@ -221,10 +225,10 @@ int final_conv_bwd_launch(const float* dout_nhwc3, const float* o, const float* 
     const int threads = (kFinalBwdThreads / c4n) * c4n;
     int nblk = kFinalBwdBlocks;
     if ((long long)nblk > P) nblk = (int)P;
-    final_conv_bwd_kernel<true><<<nblk, threads, (size_t)threads * 16 * sizeof(float), stream>>>(dout_nhwc3, o, w, d_o, P,
+    (void)launch_pdl(final_conv_bwd_kernel<true>, dim3(nblk), dim3(threads), (size_t)((size_t)threads * 16 * sizeof(float)), stream, dout_nhwc3, o, w, d_o, P,
                                                                                                C, round, scratch);
     SINDDM_CUDA_OK(cudaGetLastError());
-    final_conv_bwd_finish_kernel<<<16, 256, 0, stream>>>(scratch, nblk, C, w, dw, db, db_prev, db_prev2, 0);
+    (void)launch_pdl(final_conv_bwd_finish_kernel, dim3(16), dim3(256), (size_t)(0), stream, scratch, nblk, C, w, dw, db, db_prev, db_prev2, 0);
     SINDDM_CUDA_OK(cudaGetLastError());
     return SINDDM_OK;
 }
@@ -236,23 +240,23 @@ int wgrad_from_c3_launch(const float* x3, const float* dy, long long P, int C, f
     const int threads = (kFinalBwdThreads / c4n) * c4n;
     int nblk = kFinalBwdBlocks;
     if ((long long)nblk > P) nblk = (int)P;
-    final_conv_bwd_kernel<false><<<nblk, threads, (size_t)threads * 16 * sizeof(float), stream>>>(x3, dy, nullptr, nullptr, P,
+    (void)launch_pdl(final_conv_bwd_kernel<false>, dim3(nblk), dim3(threads), (size_t)((size_t)threads * 16 * sizeof(float)), stream, x3, dy, nullptr, nullptr, P,
                                                                                                 C, 0, scratch);
     SINDDM_CUDA_OK(cudaGetLastError());
-    final_conv_bwd_finish_kernel<<<16, 256, 0, stream>>>(scratch, nblk, C, nullptr, dw, nullptr, nullptr, nullptr, 1);
+    (void)launch_pdl(final_conv_bwd_finish_kernel, dim3(16), dim3(256), (size_t)(0), stream, scratch, nblk, C, nullptr, dw, nullptr, nullptr, nullptr, 1);
     SINDDM_CUDA_OK(cudaGetLastError());
     return SINDDM_OK;
 }
 
 int colsum_final_launch(const float* part, int nrows, int C, float* out, cudaStream_t stream) {
-    colsum_final_kernel<<<ceil_div(C, 32), dim3(32, 8), 0, stream>>>(part, nrows, C, out);
+    (void)launch_pdl(colsum_final_kernel, dim3(ceil_div(C, 32)), dim3(dim3(32, 8)), (size_t)(0), stream, part, nrows, C, out);
     SINDDM_CUDA_OK(cudaGetLastError());
     return SINDDM_OK;
 }
 
 int nchw_to_nhwc_launch(const float* src, float* dst, int B, int C, int H, int W, cudaStream_t stream) {
     const long long total = (long long)B * C * H * W;
-    nchw_to_nhwc_kernel<<<grid_for(total, 256), 256, 0, stream>>>(src, dst, B, C, H * W);
+    (void)launch_pdl(nchw_to_nhwc_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), stream, src, dst, B, C, H * W);
     SINDDM_CUDA_OK(cudaGetLastError());
     return SINDDM_OK;
 }

@@ -174,6 +174,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         else tmem_alloc(tmem_slot, kTmemCols);
     }
     if (warp == 2 && lane == 0) tmem_slot[1] = 0u;   // tiles started by the MMA warps (read by the L2 prefetcher)
+    // everything above (descriptor prefetch, barrier init, TMEM allocation) overlaps the previous kernel's tail
+    pdl_grid_sync();
     if (warp >= kEpiWarp0) {
         const int t = threadIdx.x - kEpiWarp0 * 32;
         for (int i = t; i < N; i += kEpiThreads) s_bias[i] = a.ep.bias ? a.ep.bias[i] : 0.f;
@@ -1025,8 +1027,8 @@ int tc_conv_launch(const TcConvOp& op, cudaStream_t stream) {
             return SINDDM_ERR_CUDA;
         }
     } else {
-        tc_conv_kernel<false><<<op.grid, kThreads, op.smem_bytes, stream>>>(op.tm_a, op.tm_ares, op.tm_b, op.tm_bres,
-                                                                            op.tm_out, op.tm_pre, op.tm_in, a);
+        (void)launch_pdl(tc_conv_kernel<false>, dim3(op.grid), dim3(kThreads), (size_t)op.smem_bytes, stream, op.tm_a,
+                         op.tm_ares, op.tm_b, op.tm_bres, op.tm_out, op.tm_pre, op.tm_in, a);
     }
     prof_end(stream);
     SINDDM_CUDA_OK(cudaGetLastError());

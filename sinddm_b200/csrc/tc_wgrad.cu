@@ -95,6 +95,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
+    pdl_grid_sync();   // the set-up above overlaps the previous kernel's tail; no global access before this point
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -325,7 +326,7 @@ int tc_wgrad_launch(const TcWgradOp& op, cudaStream_t stream) {
     a.partial = p.partial;
     dim3 grid(p.nsplit, op.ngroups);
     prof_begin(stream, 1, 2.0 * (double)p.B * p.H * p.W * p.ntaps * p.Cx * p.Cy);
-    tc_wgrad_kernel<<<grid, kThreads, op.smem_bytes, stream>>>(op.tm_x, op.tm_dy, a);
+    (void)launch_pdl(tc_wgrad_kernel, grid, dim3(kThreads), (size_t)op.smem_bytes, stream, op.tm_x, op.tm_dy, a);
     prof_end(stream);
     SINDDM_CUDA_OK(cudaGetLastError());
     return SINDDM_OK;

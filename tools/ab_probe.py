@@ -54,5 +54,20 @@ sample()
 e1.record()
 torch.cuda.synchronize()
 res["sample16_ms"] = round(e0.elapsed_time(e1) / 2, 2)
+# per-scale sampling time (second pass: plans and step graphs exist)
+per = []
+img = None
+for s, total in enumerate(bench.BALLOONS_T_IDEAL):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    if s == 0:
+        img = dif.sample(batch_size=bench.SAMPLE_BATCH)
+    else:
+        img = dif.sample_via_scale(bench.SAMPLE_BATCH, img, s=s, scale_mul=(1, 1), custom_sample=True, custom_img_size_idx=s,
+                                   custom_t=total)
+    b.record()
+    torch.cuda.synchronize()
+    per.append(round(a.elapsed_time(b), 2))
+res["sample_per_scale_ms"] = per
 res["env"] = {k: v for k, v in os.environ.items() if k.startswith("SINDDM_")}
 print(res)
