@@ -934,6 +934,10 @@ int tc_conv_prepare(const ConvProblem& p, TcConvOp* op) {
         device_info().max_smem_optin - 1024 /*alignment slack*/ - kTailBytes - op->nsa * op->abytes - kEpiBytes;
     int nst = budget / op->stage_bytes;
     if (nst > kMaxStagesB) nst = kMaxStagesB;
+    {
+        const char* e = getenv("SINDDM_TC_MAX_BOXES");   // diagnostic: shallower weight ring
+        if (e && atoi(e) >= 3 && atoi(e) < nst) nst = atoi(e);
+    }
     SINDDM_REQUIRE(nst >= 3, "tc_conv: not enough shared memory for the weight ring");
     op->nstages = nst;
     op->smem_bytes = op->nsa * op->abytes + nst * op->stage_bytes + kEpiBytes + kTailBytes + 1024;
