@@ -436,6 +436,18 @@ def train_legs(job, args, trainer, sizes, want_e2e=True):
         torch.cuda.synchronize()
         per_scale.append(e0.elapsed_time(e1) / 3)
     res["per_scale_ms"] = per_scale
+    # the dominant kernel per scale (two more steps each with the per-launch events on)
+    by_scale = []
+    for s in range(n_sc):
+        lib.sinddm_profile_enable(1)
+        trainer.train_step(s=s)
+        trainer.train_step(s=s)
+        torch.cuda.synchronize()
+        ms, fl, n = C.c_double(), C.c_double(), C.c_int()
+        job.capi.check(lib.sinddm_profile_collect(0, C.byref(ms), C.byref(fl), C.byref(n)), "profile_collect")
+        lib.sinddm_profile_enable(0)
+        by_scale.append(fl.value / (ms.value * 1e-3) / 1e12 if ms.value > 0 else None)
+    res["conv_tflops_by_scale"] = by_scale
     if not want_e2e:
         return res
 
@@ -495,13 +507,15 @@ def sampling_leg(job, trainer, t_ideal, global_batch, scale_mul=(1, 1)):
         job.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0, g0 = lib.sinddm_launch_count(), sdiff.graph_replayed_launches
+        passes = 3          # a pass is ~0.3 s: three back to back smooth the clock / power-cap jitter of a single one
         e0.record()
-        sample_once()
+        for _ in range(passes):
+            sample_once()
         e1.record()
         job.barrier()
-        ms = job.reduce_max(e0.elapsed_time(e1))
+        ms = job.reduce_max(e0.elapsed_time(e1)) / passes
         # kernels launched directly + kernels executed by CUDA-graph replays of the captured timestep
-        launches = int(lib.sinddm_launch_count() - l0) + int(sdiff.graph_replayed_launches - g0)
+        launches = (int(lib.sinddm_launch_count() - l0) + int(sdiff.graph_replayed_launches - g0)) // passes
         t0 = time.perf_counter()
         final = sample_once()[-1]
         host_imgs = final.cpu()                                   # images read back to the host
@@ -682,6 +696,8 @@ def run_b200_arm(args):
                      "traffic_source": traffic_src,
                      "peak_note": f"dense TF32 = half of the {peak_src} sustained bf16 cuBLAS rate",
                      "launches_timed": conv["launches"], "share_of_step": conv["ms"] / r["ms_total_profiled"],
+                     "achieved_by_scale": r["conv_tflops_by_scale"],
+                     "frac_by_scale": [(v / tf32_peak) if v else None for v in r["conv_tflops_by_scale"]],
                      "measured_in": "a second pass of the same K steps with CUDA events around each launch "
                                     f"({r['ms_total_profiled'] / args.steps:.3f} ms/step with the events on)",
                      "wgrad_kernel": {"achieved": wg_ach, "frac": (wg_ach / tf32_peak) if wg_ach else None,
