@@ -190,6 +190,16 @@ typedef struct sinddm_ddpm_step_desc {
 } sinddm_ddpm_step_desc;
 int sinddm_ddpm_step(const sinddm_ddpm_step_desc* desc, void* stream);
 
+/* Rows of a data-parallel noise draw.  The reference draws `noise = torch.randn_like(x)` for its whole batch
+ * (SinDDM/models.py:580, 455, 470); under data parallelism rank r needs rows [r*b, (r+1)*b) of the draw ONE GPU would
+ * have made.  This fills `out[0 .. count)` with elements [first, first + count) of the tensor that
+ * `torch.randn(numel_global floats)` produces on the CUDA generator state (seed, offset): torch's grid-stride kernel
+ * gives element li to thread li % stride (Philox subsequence) in round (li / stride) / 4, component (li / stride) % 4 of
+ * curand_normal4 (ATen/native/cuda/DistributionTemplates.h); stride = 256 * grid of torch's launch for numel_global
+ * (the caller computes it from the device properties and advances the generator offset as torch would). */
+int sinddm_philox_normal_rows(float* out, long long first, long long count, long long stride,
+                              unsigned long long seed, unsigned long long offset, void* stream);
+
 /* ---- optimizer step: gradient all-reduce + Adam + EMA in one kernel ------------------------------ */
 
 /* One optimizer step of MultiscaleTrainer.train (SinDDM/trainer.py:208-213: opt.step(), opt.zero_grad(), step_ema()

@@ -93,6 +93,7 @@ SIGNATURES = {
     "sinddm_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "sinddm_nhwc_to_nchw": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "sinddm_qsample_mix": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _ll, _vp]),
+    "sinddm_philox_normal_rows": (_i, [_vp, _ll, _ll, _ll, C.c_ulonglong, C.c_ulonglong, _vp]),
     "sinddm_l1_loss_workspace_bytes": (_sz, []),
     "sinddm_l1_loss": (_i, [_vp, _vp, _ll, _vp, _vp, _vp, _sz, _vp]),
     "sinddm_ddpm_step": (_i, [C.POINTER(DdpmStepDesc), _vp]),

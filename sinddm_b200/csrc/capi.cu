@@ -191,6 +191,14 @@ int sinddm_nhwc_to_nchw(const float* src, float* dst, int B, int C, int H, int W
     return nhwc_to_nchw_launch(src, dst, B, C, H, W, as_stream(stream));
 }
 
+int sinddm_philox_normal_rows(float* out, long long first, long long count, long long stride, unsigned long long seed,
+                              unsigned long long offset, void* stream) {
+    SINDDM_REQUIRE(out != nullptr, "philox_normal_rows: NULL output");
+    SINDDM_REQUIRE(first >= 0 && count >= 1 && stride >= 256 && stride % 256 == 0, "philox_normal_rows: bad range");
+    SINDDM_REQUIRE(offset % 4 == 0, "philox_normal_rows: the generator offset must be a multiple of 4");
+    return philox_normal_rows_launch(out, first, count, stride, seed, offset, as_stream(stream));
+}
+
 int sinddm_qsample_mix(const float* x_start, const float* x_orig, const float* noise, const int64_t* t,
                        const float* sqrt_ac, const float* sqrt_1mac, const float* gammas, float* out, int B,
                        long long per_sample, void* stream) {

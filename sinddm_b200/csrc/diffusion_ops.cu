@@ -8,6 +8,8 @@
 //
 // The arithmetic keeps the reference's operation order with separately rounded multiplies and adds
 // (__fmul_rn / __fadd_rn block FMA contraction) so results track the eager fp32 path to the last bits.
+#include <curand_kernel.h>
+
 #include "common.cuh"
 #include "diffusion_ops.h"
 
@@ -171,6 +173,37 @@ int ddpm_step_launch(const DdpmStepArgs& a, cudaStream_t stream) {
     SINDDM_REQUIRE(!a.reblur_mode || (a.x_tilde && a.gammas), "ddpm_step: re-blur mode needs x_tilde and gammas");
     const long long total = (long long)a.B * a.per_sample;
     (void)launch_pdl(ddpm_step_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), stream, a);
+    SINDDM_CUDA_OK(cudaGetLastError());
+    return SINDDM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// rows of torch.randn's stream (data-parallel noise shards)
+// ---------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256)
+philox_normal_rows_kernel(float* __restrict__ out, long long first, long long count, long long stride,
+                          unsigned long long seed, unsigned long long offset) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (long long)gridDim.x * blockDim.x) {
+        const long long li = first + e;
+        const long long q = li / stride;
+        const long long idx = li - q * stride;       // torch's thread index = Philox subsequence
+        const long long round = q >> 2;               // that thread's curand_normal4 call number
+        const int comp = (int)(q & 3);
+        curandStatePhilox4_32_10_t st;
+        curand_init(seed, (unsigned long long)idx, offset + 4ull * (unsigned long long)round, &st);
+        const float4 r = curand_normal4(&st);
+        out[e] = comp == 0 ? r.x : comp == 1 ? r.y : comp == 2 ? r.z : r.w;
+    }
+}
+}  // namespace
+
+int philox_normal_rows_launch(float* out, long long first, long long count, long long stride, unsigned long long seed,
+                              unsigned long long offset, cudaStream_t stream) {
+    long long want = (count + 255) / 256;
+    const long long cap = 148ll * 16;
+    philox_normal_rows_kernel<<<(unsigned)(want < cap ? (want < 1 ? 1 : want) : cap), 256, 0, stream>>>(out, first, count,
+                                                                                                        stride, seed, offset);
     SINDDM_CUDA_OK(cudaGetLastError());
     return SINDDM_OK;
 }

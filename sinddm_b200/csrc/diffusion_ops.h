@@ -31,4 +31,8 @@ struct DdpmStepArgs {
 };
 int ddpm_step_launch(const DdpmStepArgs& a, cudaStream_t stream);
 
+// elements [first, first + count) of torch.randn's Philox stream (see include/sinddm_b200.h)
+int philox_normal_rows_launch(float* out, long long first, long long count, long long stride, unsigned long long seed,
+                              unsigned long long offset, cudaStream_t stream);
+
 }  // namespace sinddm

@@ -198,6 +198,7 @@ class MultiScaleGaussianDiffusion(nn.Module):
     #    consumes exactly the random numbers the 1-GPU run would.  dp_world == 1: plain draws.
     dp_rank = 0
     dp_world = 1
+    dp_shard_rng = os.environ.get('SINDDM_DP_SHARD_RNG', '1') != '0'
 
     def set_data_parallel(self, rank, world):
         self.dp_rank, self.dp_world = int(rank), int(world)
@@ -208,6 +209,14 @@ class MultiScaleGaussianDiffusion(nn.Module):
     def _randn(self, shape, device):
         if self.dp_world == 1:
             return torch.randn(shape, device=device)
+        dev = torch.device(device)
+        numel = int(np.prod(shape)) * self.dp_world
+        if (dev.type == 'cuda' and self.dp_shard_rng and numel >= 16 and numel < 2 ** 31
+                and not torch.cuda.is_current_stream_capturing()):
+            # only this rank's rows of the global draw, same values, same generator advance (ops.randn_rows)
+            return ops.randn_rows(tuple(shape), self.dp_rank, self.dp_world, dev)
+        # CPU (gloo tests), CUDA-graph capture (the offset must come from the graph's generator state), tiny draws:
+        # draw the global batch and keep the shard
         full = torch.randn((shape[0] * self.dp_world, *shape[1:]), device=device)
         return self._shard(full, shape[0])
 

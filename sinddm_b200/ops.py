@@ -193,3 +193,35 @@ def ddpm_step(x_t, eps, noise, t, tables: dict, *, x_tilde=None, gammas_row=None
     d.gammas = ptr(gammas_row)
     check(lib.sinddm_ddpm_step(C.byref(d), _stream(x_t)), "ddpm_step")
     return out
+
+
+def randn_rows(shape, rank: int, world: int, device) -> torch.Tensor:
+    """Rows [rank*b, (rank+1)*b) of `torch.randn((b*world, *shape[1:]), device=device)` WITHOUT generating the other
+    ranks' rows: the shard is produced by a kernel that replays torch's element <-> Philox-counter mapping
+    (sinddm_philox_normal_rows), and the device generator's offset is advanced exactly as the global draw would have.
+    `shape` is the LOCAL shape (b, ...).  Values and generator state are bit-identical to draw-everything-and-slice
+    (tests/test_gpu_ops.py), so N ranks still consume the random numbers one GPU would."""
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise _capi.SinddmError("randn_rows needs a CUDA device")
+    index = dev.index if dev.index is not None else torch.cuda.current_device()
+    _capi.init(index)
+    lib = _capi.load()
+    b = int(shape[0])
+    per_row = 1
+    for d in shape[1:]:
+        per_row *= int(d)
+    count = b * per_row
+    numel = count * int(world)
+    props = torch.cuda.get_device_properties(index)
+    # ATen/native/cuda/DistributionTemplates.h::calc_execution_policy (block 256, unroll 4)
+    grid = min(props.multi_processor_count * (props.max_threads_per_multi_processor // 256), (numel + 255) // 256)
+    stride = 256 * grid
+    increment = ((numel - 1) // (stride * 4) + 1) * 4
+    gen = torch.cuda.default_generators[index]
+    seed, offset = int(gen.initial_seed()), int(gen.get_offset())
+    out = torch.empty(tuple(int(d) for d in shape), dtype=torch.float32, device=dev)
+    check(lib.sinddm_philox_normal_rows(ptr(out), int(rank) * count, count, stride, seed, offset,
+                                        torch.cuda.current_stream(dev).cuda_stream), "philox_normal_rows")
+    gen.set_offset(offset + increment)
+    return out

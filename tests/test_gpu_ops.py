@@ -268,3 +268,45 @@ def test_streamed_epilogue_operand_is_deterministic(ops):
     for _ in range(120):
         out = ops.conv_forward(x, wf, math=1, bias=bias, res_add=res)["out"]
         assert torch.equal(out, want)
+
+
+@pytest.mark.parametrize("world,b,chw", [(2, 3, (3, 5, 7)), (8, 32, (3, 186, 248)), (4, 16, (3, 133, 177)), (8, 2, (3, 48, 64)),
+                                          (3, 1, (1, 1, 17))])
+def test_data_parallel_noise_shard_equals_rows_of_the_global_draw(world, b, chw):
+    """ops.randn_rows (sinddm_philox_normal_rows): rank r's rows of torch.randn's global draw without generating the
+    rest -- values bit-identical to draw-and-slice for every rank, and the generator ends in the same state (the next
+    torch draw is unchanged).  This is what lets N ranks consume exactly the random numbers one GPU would at 1/N of the
+    cost."""
+    from sinddm_b200 import ops
+    dev = torch.device("cuda:0")
+    torch.manual_seed(1234)
+    torch.randn(5, device=dev)                      # a non-zero starting offset
+    state = torch.cuda.get_rng_state(dev)
+    full = torch.randn((b * world, *chw), device=dev)
+    after = torch.randint(0, 1000, (8,), device=dev)
+    for rank in sorted({0, world - 1, world // 2}):
+        torch.cuda.set_rng_state(state, dev)
+        rows = ops.randn_rows((b, *chw), rank, world, dev)
+        assert torch.equal(rows, full[rank * b:(rank + 1) * b]), (world, rank)
+        assert torch.equal(torch.randint(0, 1000, (8,), device=dev), after)
+
+
+def test_diffusion_randn_uses_the_shard_kernel_under_data_parallel():
+    import tempfile
+    from sinddm_b200 import MultiScaleGaussianDiffusion, SinDDMNet
+    net = SinDDMNet(dim=16, multiscale=True)
+    dif = MultiScaleGaussianDiffusion(denoise_fn=net, n_scales=2, scale_factor=1.3, image_sizes=[(23, 19), (30, 25)],
+                                      timesteps=100, train_full_t=True, scale_losses=[0.9], results_folder=tempfile.mkdtemp())
+    dev = torch.device("cuda:0")
+    for shard in (True, False):
+        dif.dp_shard_rng = shard
+        got = []
+        for rank in range(4):
+            dif.set_data_parallel(rank, 4)
+            torch.manual_seed(77)
+            got.append(dif._randn((2, 3, 25, 30), dev))
+            tail = torch.randn(3, device=dev)
+        torch.manual_seed(77)
+        full = torch.randn((8, 3, 25, 30), device=dev)
+        assert torch.equal(torch.cat(got), full)
+        assert torch.equal(tail, torch.randn(3, device=dev))
