@@ -112,6 +112,12 @@ SINDDM_DEVINL float lds_f32_plain(uint32_t addr) {
     return v;
 }
 
+SINDDM_DEVINL float4 lds_f4_plain(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
 SINDDM_DEVINL float4 lds_f4(uint32_t addr) {
     float4 v;
     asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4];"

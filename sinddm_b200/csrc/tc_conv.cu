@@ -712,10 +712,20 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                         }
                     }
                     if (ep.w_res3) {
+                        // the 16 columns' [3] weights are 48 consecutive floats (16-byte aligned: s_wres3 sits 976 B into
+                        // the 1024-aligned tail, cc * 12 B is a multiple of 192): twelve broadcast LDS.128 through the
+                        // shared window instead of 48 scalar loads through generic addresses
+                        const uint32_t wb = smem_u32(s_wres3) + (uint32_t)cc * 12u;
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const float* wr = &s_wres3[(cc + j) * 3];
-                            v[j] = fmaf(x3v[2], wr[2], fmaf(x3v[1], wr[1], fmaf(x3v[0], wr[0], v[j])));
+                        for (int g4 = 0; g4 < 4; ++g4) {          // 4 columns = 12 floats = 3 x float4 per step
+                            const float4 w0 = lds_f4_plain(wb + g4 * 48u), w1 = lds_f4_plain(wb + g4 * 48u + 16u),
+                                         w2 = lds_f4_plain(wb + g4 * 48u + 32u);
+                            const float wr[12] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w};
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj) {
+                                const int j = g4 * 4 + jj;
+                                v[j] = fmaf(x3v[2], wr[3 * jj + 2], fmaf(x3v[1], wr[3 * jj + 1], fmaf(x3v[0], wr[3 * jj], v[j])));
+                            }
                         }
                     }
                     if (ep.res_add) {
