@@ -81,17 +81,34 @@ cond_bwd_chain_kernel(const CondParams P, int B, CondSaved S, const float* __res
                       float* __restrict__ dm /*[4][B][32]*/, float* __restrict__ dcv /*[B][32]*/,
                       float* __restrict__ dh1 /*[B][128]*/) {
     pdl_grid_sync();   // programmatic dependent launch: nothing above touches global memory
-    __shared__ float s_dm[TD], s_dg2[TD], s_dcv[TD];
+    __shared__ float s_dm[TD], s_dg2[TD], s_dcv[TD], s_part[4][TD];
     const int b = blockIdx.x, t = threadIdx.x;
     if (t < TD) s_dg2[t] = 0.f;
     __syncthreads();
     size_t coff = 0;
     for (int l = 0; l < kNumBlocks; ++l) {
         const int C = P.C[l];
-        if (t < TD) {
-            float acc = 0.f;
+        {
+            // dm = Wt^T dcond: the channel range is split over the block's four warps (this loop used to run on one
+            // warp as a chain of C dependent global loads + FMAs: 80 us per training step at every scale), partial sums
+            // are combined in a fixed order
+            const int part = t >> 5, lane = t & 31;
+            const int per = (C + 3) / 4;
+            const int c0 = part * per, c1 = min(C, c0 + per);
             const float* g = dcond + coff + (size_t)b * C;
-            for (int c = 0; c < C; ++c) acc = fmaf(P.wt[l][(size_t)c * TD + t], g[c], acc);
+            const float* w = P.wt[l] + lane;
+            float a0 = 0.f, a1 = 0.f;
+            int c = c0;
+            for (; c + 1 < c1; c += 2) {
+                a0 = fmaf(w[(size_t)c * TD], g[c], a0);
+                a1 = fmaf(w[(size_t)(c + 1) * TD], g[c + 1], a1);
+            }
+            if (c < c1) a0 = fmaf(w[(size_t)c * TD], g[c], a0);
+            s_part[part][lane] = a0 + a1;
+        }
+        __syncthreads();
+        if (t < TD) {
+            const float acc = ((s_part[0][t] + s_part[1][t]) + s_part[2][t]) + s_part[3][t];
             s_dm[t] = acc;
             dm[((size_t)l * B + b) * TD + t] = acc;
         }

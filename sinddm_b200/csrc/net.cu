@@ -391,42 +391,42 @@ int net_pack_weights(Plan* pl, const float* const* params, cudaStream_t s) {
         explicit PdlScope(long long px) { pdl_set(px <= pdl_max_pixels()); }
         ~PdlScope() { pdl_set(false); }
     } pdl_scope(pl->P);
+    // every repack of the step goes into ONE launch (pack_jobs_kernel)
+    PackJobs jobs;
+    jobs.n = 0;
     for (int l = 0; l < kNumBlocks; ++l) {
         BlockBufs& b = pl->blk[l];
         // tensor-core layers read the blocked pre-swizzled layout, CUDA-core layers the plain [tap][N][K] one
         if (b.im2col) {
-            SINDDM_TRY(pack_im2col_weights_launch(params[b.pbase + 6], b.Co, b.w0_f, rnd, pl->blocked_weights, s));
+            pack_jobs_add_im2col(&jobs, params[b.pbase + 6], b.Co, b.w0_f, rnd, pl->blocked_weights);
             if (pl->training)
-                SINDDM_TRY(pack_conv_weights_launch(params[b.pbase + 6], b.Co, b.Ci, 9, nullptr, b.w0_d, rnd && b.tc_d1, s,
-                                                    b.tc_d1 && pl->blocked_weights, b.pd1.N));
+                pack_jobs_add_conv(&jobs, params[b.pbase + 6], b.Co, b.Ci, 9, nullptr, b.w0_d, rnd && b.tc_d1,
+                                   b.tc_d1 && pl->blocked_weights, b.pd1.N);
         } else if (pl->training && b.tc_d1 != b.tc_c1) {
             // l1: the forward conv (Cin = 3) runs on CUDA cores, its data gradient on the tensor cores
-            SINDDM_TRY(pack_conv_weights_launch(params[b.pbase + 6], b.Co, b.Ci, 9, b.w0_f, nullptr, rnd && b.tc_c1, s,
-                                                b.tc_c1 && pl->blocked_weights));
-            SINDDM_TRY(pack_conv_weights_launch(params[b.pbase + 6], b.Co, b.Ci, 9, nullptr, b.w0_d, rnd && b.tc_d1, s,
-                                                b.tc_d1 && pl->blocked_weights, b.pd1.N));
+            pack_jobs_add_conv(&jobs, params[b.pbase + 6], b.Co, b.Ci, 9, b.w0_f, nullptr, rnd && b.tc_c1,
+                               b.tc_c1 && pl->blocked_weights);
+            pack_jobs_add_conv(&jobs, params[b.pbase + 6], b.Co, b.Ci, 9, nullptr, b.w0_d, rnd && b.tc_d1,
+                               b.tc_d1 && pl->blocked_weights, b.pd1.N);
         } else {
-            SINDDM_TRY(pack_conv_weights_launch(params[b.pbase + 6], b.Co, b.Ci, 9, b.w0_f, b.w0_d, rnd && b.tc_c1, s,
-                                                b.tc_c1 && pl->blocked_weights, pl->training ? b.pd1.N : 0));
+            pack_jobs_add_conv(&jobs, params[b.pbase + 6], b.Co, b.Ci, 9, b.w0_f, b.w0_d, rnd && b.tc_c1,
+                               b.tc_c1 && pl->blocked_weights, pl->training ? b.pd1.N : 0);
         }
-        SINDDM_TRY(pack_conv_weights_launch(params[b.pbase + 8], b.Co, b.Co, 9, b.w2_f, b.w2_d, rnd && b.tc_c2, s,
-                                            b.tc_c2 && pl->blocked_weights));
+        pack_jobs_add_conv(&jobs, params[b.pbase + 8], b.Co, b.Co, 9, b.w2_f, b.w2_d, rnd && b.tc_c2,
+                           b.tc_c2 && pl->blocked_weights);
         if (b.has_res) {
             if (b.Ci >= 8)
-                SINDDM_TRY(pack_conv_weights_launch(params[b.pbase + 10], b.Co, b.Ci, 1, b.wr_f, b.wr_d,
-                                                    rnd && b.tc_c2, s, b.tc_c2 && pl->blocked_weights));
+                pack_jobs_add_conv(&jobs, params[b.pbase + 10], b.Co, b.Ci, 1, b.wr_f, b.wr_d, rnd && b.tc_c2,
+                                   b.tc_c2 && pl->blocked_weights);
             // net[2].bias + res_conv.bias enter the same epilogue
-            (void)launch_pdl(add_vec_kernel, dim3(ceil_div(b.Co, 128)), dim3(128), (size_t)(0), s, params[b.pbase + 9], params[b.pbase + 11], b.bias2c,
-                                                              b.Co);
-            SINDDM_CUDA_OK(cudaGetLastError());
+            pack_jobs_add_sum(&jobs, params[b.pbase + 9], params[b.pbase + 11], b.bias2c, b.Co);
         }
     }
     if (pl->training) {
         // final_conv.0.weight [3][half] -> data-gradient layout [1][half][3]
-        SINDDM_TRY(
-            pack_conv_weights_launch(params[kNumParams - 2], pl->channels, pl->half, 1, nullptr, pl->wf_d, 0, s));
+        pack_jobs_add_conv(&jobs, params[kNumParams - 2], pl->channels, pl->half, 1, nullptr, pl->wf_d, 0);
     }
-    return SINDDM_OK;
+    return pack_jobs_launch(&jobs, s);
 }
 
 static void fill_cond_params(const Plan* pl, const float* const* params, CondParams* cp) {

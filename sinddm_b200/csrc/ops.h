@@ -126,6 +126,29 @@ int pack_conv_weights_launch(const float* w, int Cout, int Cin, int ntaps, float
 // gradient of that GEMM back to OIHW.
 int im2col3x3_c3_launch(const float* x, float* out, int B, int H, int W, int round, cudaStream_t stream);
 int pack_im2col_weights_launch(const float* w, int Co, float* dst, int round, int blocked, cudaStream_t stream);
+// All weight-packing work of one step in ONE launch (they used to be ~15 launches of a few microseconds each, every
+// training step, at every scale).  kind 0: pack_conv_weights, 1: pack_im2col_weights, 2: o = a + b (bias sums).
+struct PackJob {
+    int kind;
+    const float* w;        // source (kind 2: a)
+    const float* w2;       // kind 2: b
+    float* dst_fwd;        // kind 1: dst; kind 2: o
+    float* dst_dgrad;
+    int Cout, Cin, ntaps, round, blocked, dgrad_rows;
+    int total;             // elements (threads) of this job
+    int block0;            // first 256-thread block of this job (filled by the launcher)
+};
+constexpr int kMaxPackJobs = 20;
+struct PackJobs {
+    PackJob j[kMaxPackJobs];
+    int n;
+};
+void pack_jobs_add_conv(PackJobs* jobs, const float* w, int Cout, int Cin, int ntaps, float* dst_fwd, float* dst_dgrad,
+                        int round, int blocked = 0, int dgrad_rows = 0);
+void pack_jobs_add_im2col(PackJobs* jobs, const float* w, int Co, float* dst, int round, int blocked);
+void pack_jobs_add_sum(PackJobs* jobs, const float* a, const float* b, float* o, int n);
+int pack_jobs_launch(PackJobs* jobs, cudaStream_t stream);
+
 // floats needed by a packed weight buffer in either layout ([ntaps][N][K] or blocked with K padded to 32)
 inline size_t packed_weight_floats(int ntaps, int N, int K) { return (size_t)ntaps * N * ((K + 31) / 32 * 32); }
 

@@ -6,6 +6,8 @@
 // runs here with plain FFMA so results can be checked against the CPU oracle at fp32 tolerance and the
 // tcgen05 kernels can be checked against an exact on-device twin.  Same ConvProblem / WgradProblem
 // contract as the tensor-core kernels, including every epilogue option.
+#include <string.h>
+
 #include "common.cuh"
 #include "ops.h"
 
@@ -223,13 +225,9 @@ __device__ __forceinline__ size_t packed_index(int tap, int n, int k, int N, int
     return (((size_t)tap * nchunk + chunk) * N + n) * 32 + grp * 4 + (kk & 3);
 }
 
-__global__ void pack_conv_weights_kernel(const float* __restrict__ w, int Cout, int Cin, int ntaps,
-                                         float* __restrict__ dst_fwd, float* __restrict__ dst_dgrad, int round,
-                                         int blocked, int dgrad_rows) {
-    pdl_grid_sync();   // programmatic dependent launch: nothing above touches global memory
-    const int total = Cout * Cin * ntaps;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
+__device__ __forceinline__ void pack_conv_one(int i, const float* __restrict__ w, int Cout, int Cin, int ntaps,
+                                              float* __restrict__ dst_fwd, float* __restrict__ dst_dgrad, int round,
+                                              int blocked, int dgrad_rows) {
     const int tap = i % ntaps;
     const int ci = (i / ntaps) % Cin;
     const int co = i / (ntaps * Cin);
@@ -237,6 +235,35 @@ __global__ void pack_conv_weights_kernel(const float* __restrict__ w, int Cout, 
     if (round) v = round_tf32(v);
     if (dst_fwd) dst_fwd[packed_index(tap, co, ci, Cout, Cin, blocked)] = v;
     if (dst_dgrad) dst_dgrad[packed_index(ntaps - 1 - tap, ci, co, dgrad_rows, Cout, blocked)] = v;
+}
+
+__global__ void __launch_bounds__(256) pack_jobs_kernel(const PackJobs jobs) {
+    pdl_grid_sync();   // programmatic dependent launch: nothing above touches global memory
+    int k = 0;
+    while (k + 1 < jobs.n && (int)blockIdx.x >= jobs.j[k + 1].block0) ++k;
+    const PackJob& J = jobs.j[k];
+    const int i = ((int)blockIdx.x - J.block0) * 256 + (int)threadIdx.x;
+    if (i >= J.total) return;
+    if (J.kind == 0) {
+        pack_conv_one(i, J.w, J.Cout, J.Cin, J.ntaps, J.dst_fwd, J.dst_dgrad, J.round, J.blocked, J.dgrad_rows);
+    } else if (J.kind == 1) {
+        const int tap = i % 9, c = (i / 9) % 3, co = i / 27;
+        float v = J.w[i];
+        if (J.round) v = round_tf32(v);
+        J.dst_fwd[packed_index(0, co, tap * 3 + c, J.Cout, 32, J.blocked)] = v;
+    } else {
+        J.dst_fwd[i] = J.w[i] + J.w2[i];
+    }
+}
+
+__global__ void pack_conv_weights_kernel(const float* __restrict__ w, int Cout, int Cin, int ntaps,
+                                         float* __restrict__ dst_fwd, float* __restrict__ dst_dgrad, int round,
+                                         int blocked, int dgrad_rows) {
+    pdl_grid_sync();   // programmatic dependent launch: nothing above touches global memory
+    const int total = Cout * Cin * ntaps;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    pack_conv_one(i, w, Cout, Cin, ntaps, dst_fwd, dst_dgrad, round, blocked, dgrad_rows);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -828,6 +855,47 @@ int pack_conv_weights_launch(const float* w, int Cout, int Cin, int ntaps, float
     const int total = Cout * Cin * ntaps;
     (void)launch_pdl(pack_conv_weights_kernel, dim3(ceil_div(total, 256)), dim3(256), (size_t)(0), stream, w, Cout, Cin, ntaps, dst_fwd, dst_dgrad, round,
                                                                        blocked, dgrad_rows > Cin ? dgrad_rows : Cin);
+    SINDDM_CUDA_OK(cudaGetLastError());
+    return SINDDM_OK;
+}
+
+static PackJob* pack_jobs_next(PackJobs* jobs) {
+    if (jobs->n >= kMaxPackJobs) return nullptr;
+    PackJob* j = &jobs->j[jobs->n++];
+    memset(j, 0, sizeof(*j));
+    return j;
+}
+
+void pack_jobs_add_conv(PackJobs* jobs, const float* w, int Cout, int Cin, int ntaps, float* dst_fwd, float* dst_dgrad,
+                        int round, int blocked, int dgrad_rows) {
+    PackJob* j = pack_jobs_next(jobs);
+    if (!j) return;
+    j->kind = 0; j->w = w; j->Cout = Cout; j->Cin = Cin; j->ntaps = ntaps; j->dst_fwd = dst_fwd; j->dst_dgrad = dst_dgrad;
+    j->round = round; j->blocked = blocked; j->dgrad_rows = dgrad_rows > Cin ? dgrad_rows : Cin;
+    j->total = Cout * Cin * ntaps;
+}
+
+void pack_jobs_add_im2col(PackJobs* jobs, const float* w, int Co, float* dst, int round, int blocked) {
+    PackJob* j = pack_jobs_next(jobs);
+    if (!j) return;
+    j->kind = 1; j->w = w; j->Cout = Co; j->dst_fwd = dst; j->round = round; j->blocked = blocked; j->total = Co * 27;
+}
+
+void pack_jobs_add_sum(PackJobs* jobs, const float* a, const float* b, float* o, int n) {
+    PackJob* j = pack_jobs_next(jobs);
+    if (!j) return;
+    j->kind = 2; j->w = a; j->w2 = b; j->dst_fwd = o; j->total = n;
+}
+
+int pack_jobs_launch(PackJobs* jobs, cudaStream_t stream) {
+    SINDDM_REQUIRE(jobs->n < kMaxPackJobs, "pack_jobs: too many jobs");
+    if (jobs->n == 0) return SINDDM_OK;
+    int blocks = 0;
+    for (int k = 0; k < jobs->n; ++k) {
+        jobs->j[k].block0 = blocks;
+        blocks += ceil_div(jobs->j[k].total, 256);
+    }
+    (void)launch_pdl(pack_jobs_kernel, dim3(blocks), dim3(256), (size_t)0, stream, *jobs);
     SINDDM_CUDA_OK(cudaGetLastError());
     return SINDDM_OK;
 }
