@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(128)
 cond_fwd_kernel(const CondParams P, const long long* __restrict__ time, float scale, const float* __restrict__ freqs,
                 int B, CondSaved S, float* __restrict__ cond) {
     pdl_grid_sync();   // programmatic dependent launch: nothing above touches global memory
-    __shared__ float emb[ED], g1[HD], g2[TD], m[TD];
+    __shared__ float emb[ED], g1[HD], g2[TD];
     const int b = blockIdx.x, t = threadIdx.x;
 
     if (t < ED) {
@@ -36,7 +36,7 @@ cond_fwd_kernel(const CondParams P, const long long* __restrict__ time, float sc
     {   // time_mlp.0 : Linear(64 -> 128), then GELU
         float acc = P.w0b[t];
         const float* wr = P.w0 + (size_t)t * ED;
-#pragma unroll 8
+#pragma unroll 32
         for (int k = 0; k < ED; ++k) acc = fmaf(wr[k], emb[k], acc);
         S.h1[(size_t)b * HD + t] = acc;
         g1[t] = gelu_erf(acc);
@@ -45,33 +45,50 @@ cond_fwd_kernel(const CondParams P, const long long* __restrict__ time, float sc
     if (t < TD) {  // time_mlp.2 : Linear(128 -> 32) = cond_vec; every block starts with GELU(cond_vec)
         float acc = P.w2b[t];
         const float* wr = P.w2 + (size_t)t * HD;
-#pragma unroll 8
+#pragma unroll 32
         for (int k = 0; k < HD; ++k) acc = fmaf(wr[k], g1[k], acc);
         S.cv[(size_t)b * TD + t] = acc;
         g2[t] = gelu_erf(acc);
     }
     __syncthreads();
-    size_t coff = 0;
-    for (int l = 0; l < kNumBlocks; ++l) {
-        if (t < TD) {  // block.mlp[1] : Linear(32 -> 32)
-            float acc = P.wmb[l][t];
-            const float* wr = P.wm[l] + (size_t)t * TD;
+    // The four blocks' conditioning heads only depend on g2: warp l computes block l's mlp[1] (Linear 32 -> 32), then
+    // all sum(C_l) time_reshape outputs (Conv1x1 32 -> C on a 1x1 image) are spread over the block.  Same summation
+    // order per output as the sequential form (bias first, k ascending): bit-identical results, two phases instead of
+    // eight (this kernel is on the critical path of every sampling step: 246 launches per image batch).
+    static_assert(kNumBlocks * TD == 128, "cond_fwd_kernel runs 128 threads: one warp per block's mlp[1]");
+    __shared__ float m_all[kNumBlocks][TD];
+    {
+        const int l = t >> 5, j = t & 31;   // blockDim.x == 128 == kNumBlocks * TD
+        float acc = P.wmb[l][j];
+        const float* wr = P.wm[l] + (size_t)j * TD;
+        float wv[TD];
 #pragma unroll
-            for (int k = 0; k < TD; ++k) acc = fmaf(wr[k], g2[k], acc);
-            m[t] = acc;
-            S.m[((size_t)l * B + b) * TD + t] = acc;
+        for (int k = 0; k < TD; ++k) wv[k] = wr[k];
+#pragma unroll
+        for (int k = 0; k < TD; ++k) acc = fmaf(wv[k], g2[k], acc);
+        m_all[l][j] = acc;
+        S.m[((size_t)l * B + b) * TD + j] = acc;
+    }
+    __syncthreads();
+    int ctot = 0;
+    for (int l = 0; l < kNumBlocks; ++l) ctot += P.C[l];
+    for (int o = t; o < ctot; o += blockDim.x) {
+        int l = 0, c = o;
+        size_t coff = 0;
+        while (c >= P.C[l]) {
+            c -= P.C[l];
+            coff += (size_t)B * P.C[l];
+            ++l;
         }
-        __syncthreads();
         const int C = P.C[l];
-        for (int c = t; c < C; c += blockDim.x) {  // block.time_reshape : Conv1x1(32 -> C) on a 1x1 image
-            float acc = P.wtb[l][c];
-            const float* wr = P.wt[l] + (size_t)c * TD;
+        float acc = P.wtb[l][c];
+        const float* wr = P.wt[l] + (size_t)c * TD;
+        float wv[TD];
 #pragma unroll
-            for (int k = 0; k < TD; ++k) acc = fmaf(wr[k], m[k], acc);
-            cond[coff + (size_t)b * C + c] = acc;
-        }
-        coff += (size_t)B * C;
-        __syncthreads();
+        for (int k = 0; k < TD; ++k) wv[k] = wr[k];
+#pragma unroll
+        for (int k = 0; k < TD; ++k) acc = fmaf(wv[k], m_all[l][k], acc);
+        cond[coff + (size_t)b * C + c] = acc;
     }
 }
 
