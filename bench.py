@@ -427,14 +427,15 @@ def train_legs(job, args, trainer, sizes, want_e2e=True):
     per_scale = []
     for s in range(n_sc):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 6 if s < n_sc - 2 else 3        # short loops expose the first step's host launch latency at small scales
         trainer.train_step(s=s)
         torch.cuda.synchronize()
         e0.record()
-        for _ in range(3):
+        for _ in range(reps):
             trainer.train_step(s=s)
         e1.record()
         torch.cuda.synchronize()
-        per_scale.append(e0.elapsed_time(e1) / 3)
+        per_scale.append(e0.elapsed_time(e1) / reps)
     res["per_scale_ms"] = per_scale
     # the dominant kernel per scale (two more steps each with the per-launch events on)
     by_scale = []

@@ -107,6 +107,9 @@ class _Runtime:
         self.freqs = {}
         self.weights_epoch = 0      # bumped when a kernel updated the parameters in place (fused optimizer step)
         self.grad_bucket = None     # flat fp32 tensor backward writes the 52 gradients into (fused optimizer step)
+        self.param_offsets = None   # element offset of every parameter inside that bucket (parameter order)
+        self.param_total = 0
+        self.param_list = None      # cached list(self.parameters()) (the Parameter objects never change)
 
     def __deepcopy__(self, memo):
         return _Runtime()
@@ -156,9 +159,17 @@ class _NetFunction(torch.autograd.Function):
             ctx.plan = plan
             ctx.generation = plan.generation
             bucket = net._runtime.grad_bucket
-            if bucket is not None and bucket.numel() != sum(p.numel() for p in params):
+            offsets = net._runtime.param_offsets
+            if offsets is None or len(offsets) != len(params):
+                offsets, total = [], 0
+                for p in params:
+                    offsets.append(total)
+                    total += p.numel()
+                net._runtime.param_offsets, net._runtime.param_total = offsets, total
+            if bucket is not None and bucket.numel() != net._runtime.param_total:
                 raise _capi.SinddmError("gradient bucket size does not match the parameters")
             ctx.grad_bucket = bucket
+            ctx.param_offsets = offsets
             ctx.save_for_backward(*params)
         return out
 
@@ -173,17 +184,24 @@ class _NetFunction(torch.autograd.Function):
         lib = _capi.load()
         dout = dout.contiguous()
         stream = torch.cuda.current_stream(dout.device).cuda_stream
-        sizes = [p.numel() for p in params]
         bucket = ctx.grad_bucket
-        flat = bucket if bucket is not None else torch.empty(sum(sizes), dtype=torch.float32, device=dout.device)
-        views = list(flat.split(sizes))
-        grads = [v.view_as(p) for v, p in zip(views, params)]
+        if bucket is not None:
+            # fused optimizer step: the 52 gradients go straight into the flat bucket at fixed offsets (no tensor views:
+            # this runs between the loss read-back and the first backward kernel, i.e. on the critical path of a step),
+            # stay there for sinddm_fused_step, and autograd does not accumulate them into .grad
+            offsets = ctx.param_offsets
+            base = bucket.data_ptr()
+            garr = (C.c_void_p * NUM_PARAMS)()
+            for i, off in enumerate(offsets):
+                garr[i] = base + 4 * off
+            check(lib.sinddm_net_backward(plan.handle, _ptr_array(params), dout.data_ptr(), garr, stream),
+                  "sinddm_net_backward")
+            return (None,) * (5 + len(params))
+        sizes = [p.numel() for p in params]
+        flat = torch.empty(sum(sizes), dtype=torch.float32, device=dout.device)
+        grads = [v.view_as(p) for v, p in zip(flat.split(sizes), params)]
         check(lib.sinddm_net_backward(plan.handle, _ptr_array(params), dout.data_ptr(), _ptr_array(grads), stream),
               "sinddm_net_backward")
-        if bucket is not None:
-            # fused optimizer step: the gradients stay in the bucket (consumed by sinddm_fused_step), autograd
-            # does not accumulate them into .grad
-            return (None,) * (5 + len(params))
         return (None, None, None, None, None, *grads)
 
 
@@ -256,9 +274,14 @@ class SinDDMNet(nn.Module):
         if not x.is_cuda:
             raise _capi.SinddmError("SinDDMNet.forward needs CUDA tensors: sinddm_b200 has no CPU fallback")
         _capi.init(x.device.index if x.device.index is not None else torch.cuda.current_device())
-        params = list(self.parameters())
-        if len(params) != NUM_PARAMS:
-            raise _capi.SinddmError(f"expected {NUM_PARAMS} parameter tensors, found {len(params)}")
+        params = self._runtime.param_list
+        if params is not None and not (params[0] is self.time_mlp[0].weight and params[-1] is self.final_conv[0].bias):
+            params = None               # a Parameter object was replaced: rebuild the cached list
+        if params is None:
+            params = list(self.parameters())
+            if len(params) != NUM_PARAMS:
+                raise _capi.SinddmError(f"expected {NUM_PARAMS} parameter tensors, found {len(params)}")
+            self._runtime.param_list = params
         x = x.contiguous().float()
         time = time.contiguous().to(torch.int64)
         scale_val = float(scale.item()) if torch.is_tensor(scale) else float(scale)

@@ -333,7 +333,9 @@ class MultiscaleTrainer(object):
                 self._loss_acc_host += self.last_loss
             else:
                 self._loss_acc += loss.detach().double()
-            loss_backwards(self.fp16, loss / self.gradient_accumulate_every, self.opt)
+            # (loss / 1 is the identity in fp32: skip the extra kernel and autograd node on the critical path)
+            loss_backwards(self.fp16, loss if self.gradient_accumulate_every == 1 else
+                           loss / self.gradient_accumulate_every, self.opt)
         if fused is None:
             self.bucket.all_reduce_mean()
         else:
