@@ -12,8 +12,6 @@
 // (Cin >= 8 and N % 16 == 0); the 3-channel layers and math == MATH_FP32 use the CUDA-core twin.
 #include "net.h"
 
-#include "common.cuh"
-
 #include <stdlib.h>
 #include <string.h>
 
@@ -376,13 +374,6 @@ int plan_build(Plan* pl, int B, int H, int W, int dim, int channels, int math, i
         fw.nsplit = simt_wgrad_nsplit(B, H, W, channels, pl->half, 1);
     }
     return SINDDM_OK;
-}
-
-__global__ void add_vec_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o,
-                               int n) {
-    pdl_grid_sync();   // programmatic dependent launch: nothing above touches global memory
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) o[i] = a[i] + b[i];
 }
 
 int net_pack_weights(Plan* pl, const float* const* params, cudaStream_t s) {
