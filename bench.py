@@ -453,9 +453,11 @@ def train_legs(job, args, trainer, sizes, want_e2e=True):
         return res
 
     # ---- end to end: MultiscaleTrainer.train() itself, inputs resident on the HOST, loss read back every step
-    trainer.host_data = True
-    trainer.data_list = [tuple(trainer._place(t.cpu()) for t in pair) for pair in trainer.data_list]
+    trainer.prepare_host_data()             # pinned host batches + persistent device staging buffers for every scale
     trainer.loss_readback = "step"
+    for i in range(2 * n_sc):               # every scale twice in this mode before anything is seeded or timed
+        trainer.train_step(s=i % n_sc)
+    torch.cuda.synchronize()
     res["h2d"] = float(np.mean([sum(t.numel() * 4 for t in pair) for pair in trainer.data_list]))
     e2e_warm = max(args.warmup, 10)
     seed, predicted = pick_balanced_seed(trainer, job, sizes, args.steps, e2e_warm)

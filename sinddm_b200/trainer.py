@@ -101,6 +101,9 @@ class MultiscaleTrainer(object):
             raise ValueError("loss_readback must be 'window' or 'step'")
         self.loss_readback = loss_readback
         self.last_loss = None
+        self._copy_stream = None         # host_data: side stream + persistent device staging buffers per scale
+        self._staging = {}
+        self._staging_pending = None
         self.batch_size = train_batch_size           # GLOBAL batch (split over ranks under torchrun)
         self.n_scales = n_scales
         self.scale_factor = scale_factor
@@ -145,6 +148,8 @@ class MultiscaleTrainer(object):
                 orig = ds.batch(self.local_batch)
                 self.data_list.append((self._place(orig), self._place(orig.clone())))
 
+        if self.host_data:
+            self.prepare_host_data()
         self.opt = Adam(ms_diffusion_model.parameters(), lr=train_lr)
         self.scheduler = MultiStepLR(self.opt, milestones=self.sched_milestones, gamma=0.5)
         self.bucket = spdist.GradientBucket(ms_diffusion_model.parameters())
@@ -155,7 +160,6 @@ class MultiscaleTrainer(object):
         self.running_scale = []
         self.avg_t = []
         self.scale_counts = [0] * (n_scales or 0)      # new: how often train_step ran each scale
-        self._copy_stream = None
 
         assert not fp16, 'Apex must be installed in order for mixed precision training to be turned on'
         self.fp16 = fp16
@@ -169,23 +173,49 @@ class MultiscaleTrainer(object):
             return batch.contiguous().pin_memory() if torch.cuda.is_available() else batch.contiguous()
         return batch.to(self.device)
 
+    def prepare_host_data(self):
+        """host_data=True: move every scale's batch to pinned host memory (if it is not there yet) and allocate the
+        persistent device staging buffers of all scales NOW, so that no step of the training loop allocates (a
+        cudaMalloc in the middle of a run stalls the host for tens of milliseconds)."""
+        self.host_data = True
+        self.data_list = [tuple(t if (not t.is_cuda and t.is_pinned()) else self._place(t.cpu()) for t in pair)
+                          for pair in self.data_list]
+        if torch.cuda.is_available() and self.data_list and self.data_list[0][0].is_pinned():
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=self.device)
+            for s, pair in enumerate(self.data_list):
+                if s not in self._staging:
+                    self._staging[s] = {'buf': [tuple(torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in pair)
+                                                for _ in range(2)], 'read': [None, None], 'i': 0}
+
     def _batch(self, s):
         pair = self.data_list[s]
         if not self.host_data:
             return pair
         if not pair[0].is_pinned():
             return tuple(t.to(self.device) for t in pair)
-        # copy on a side stream: the transfer overlaps the previous step's kernels still queued on the training
-        # stream, which only waits for the copy's completion event
+        # copy on a side stream into PERSISTENT device buffers (two per scale, alternating): the transfer overlaps
+        # the previous step's kernels still queued on the training stream, and no allocator call sits on the step's
+        # path (allocating the destination per step made the caching allocator call cudaMalloc on the copy stream's
+        # pool now and then: sporadic 25-50 ms host stalls, tools/e2e_probe.py)
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
+        st = self._staging.get(s)
+        if st is None:
+            st = {'buf': [tuple(torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in pair) for _ in range(2)],
+                  'read': [None, None], 'i': 0}
+            self._staging[s] = st
+        i = st['i']
+        st['i'] = i ^ 1
         main = torch.cuda.current_stream(self.device)
+        if st['read'][i] is not None:
+            self._copy_stream.wait_event(st['read'][i])      # the step that last read this buffer has consumed it
         with torch.cuda.stream(self._copy_stream):
-            out = tuple(t.to(self.device, non_blocking=True) for t in pair)
+            for dst, src in zip(st['buf'][i], pair):
+                dst.copy_(src, non_blocking=True)
         main.wait_stream(self._copy_stream)
-        for t in out:
-            t.record_stream(main)
-        return out
+        self._staging_pending = (st, i)                       # train_step records the "consumed" event after the forward
+        return st['buf'][i]
 
     def reset_parameters(self):
         self.ema_model.load_state_dict(self.model.state_dict())
@@ -328,6 +358,13 @@ class MultiscaleTrainer(object):
         for _ in range(self.gradient_accumulate_every):
             batch = self._batch(s)
             loss = self.model(batch, s)
+            pending = getattr(self, '_staging_pending', None)
+            if pending is not None:      # the batch is only read by the forward pass (q_sample / blur mix)
+                st, i = pending
+                if st['read'][i] is None:
+                    st['read'][i] = torch.cuda.Event()
+                st['read'][i].record(torch.cuda.current_stream(self.device))
+                self._staging_pending = None
             if self.loss_readback == 'step':
                 self.last_loss = loss.item()                # the reference's per-micro-step host sync (trainer.py:202)
                 self._loss_acc_host += self.last_loss

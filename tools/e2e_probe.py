@@ -69,6 +69,35 @@ def main():
         print("seed", seed, "predicted counts", predicted, flush=True)
         torch.manual_seed(seed)
         stamps = []
+        # phase timers: anything on the host that takes > 3 ms is reported with its name
+        slow = []
+
+        def timed(obj, name, label):
+            fn = getattr(obj, name)
+
+            def wrapper(*a, **k):
+                t0 = time.perf_counter()
+                out = fn(*a, **k)
+                dt = time.perf_counter() - t0
+                if dt > 3e-3:
+                    slow.append((label, round(1e3 * dt, 2), tr.step))
+                return out
+            setattr(obj, name, wrapper)
+        timed(tr, "_draw_scale", "draw_scale")
+        timed(tr, "_batch", "batch_copy")
+        timed(tr.model, "forward", "diffusion.forward(enqueue)")
+        timed(tr._fused, "step", "fused.step(enqueue)")
+        timed(tr.scheduler, "step", "scheduler.step")
+        import sinddm_b200.trainer as T
+        orig_bw = T.loss_backwards
+
+        def bw(*a, **k):
+            t0 = time.perf_counter()
+            orig_bw(*a, **k)
+            dt = time.perf_counter() - t0
+            if dt > 3e-3:
+                slow.append(("backward(enqueue)", round(1e3 * dt, 2), tr.step))
+        T.loss_backwards = bw
         inner = tr.train_step
 
         def stamped():
@@ -90,6 +119,7 @@ def main():
             dt = time.perf_counter() - t0
         print(f"train() {1e3 * dt / steps:.3f} ms/step, counts {tr.scale_counts}", flush=True)
         print("per-step host ms:", " ".join(f"{1e3 * a:.1f}" for a, _ in stamps[warm:]), flush=True)
+        print("slow host phases (> 3 ms; loss.item() waits are not wrapped):", slow, flush=True)
         return
     seq = [i % 5 for i in range(steps)]
     run("round robin, device data, window readback", False, "window", "device", seq=seq)
