@@ -356,6 +356,7 @@ def pick_balanced_seed(trainer, job, sizes, steps, warmup, max_seeds=600):
     px = [w * h for (w, h) in sizes]
     target = steps * float(np.mean(px))
     best = None
+    max_seeds = max(20, min(max_seeds, 12000 // (warmup + steps)))      # bound the search to a few seconds
     for seed in range(max_seeds):
         torch.manual_seed(seed)
         counts = [0] * len(sizes)
