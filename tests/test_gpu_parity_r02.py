@@ -258,3 +258,27 @@ def test_full_sampling_chain_vs_oracle_cfg3(math):
     # 4x (fp32: a handful of ulps after 246 chained evaluations)
     bound = 1e-5 if math == "fp32" else 5e-3
     assert max(errs) <= bound, errs
+
+
+@pytest.mark.parametrize("case", [("seascape finest (configs[3])", 200, 249, 3), ("starry_night x(2,2) finest (configs[4])", 396, 504, 4),
+                                  ("starry_night x(2,2) coarsest", 98, 124, 0)])
+@pytest.mark.parametrize("math", ["fp32", "tf32"])
+def test_other_baseline_shapes_vs_oracle(case, math):
+    """The denoiser at the image sizes of BASELINE configs[3] / configs[4] (not multiples of any tile size; 396x504 is
+    4x the pixels of balloons' finest scale) against the CPU oracle, B = 2 with different timesteps per row."""
+    from oracle import sinddm_oracle as orc
+    _, H, W, s = case
+    params = orc.synthetic_params(seed=11, dim=160)
+    net, _ = build(math, [(W, H)], [], params)
+    x = rs_tensor(31 + H, (2, 3, H, W), 0.5).clamp(-1, 1)
+    t = torch.tensor([3, 77])
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        ref = orc.net_forward(params, x, t, s)
+        got = net(x.to(DEV), t.to(DEV), s).cpu()
+    e_max, e_l2 = max_err_rel(got, ref), rel_err(got, ref)
+    print(f"{case[0]} {math}: max-err/max {e_max:.2e}, rel L2 {e_l2:.2e}")
+    if math == "fp32":
+        assert e_max <= 2e-4
+    else:
+        assert e_max <= 3e-2 and e_l2 <= 5e-3
