@@ -228,6 +228,9 @@ typedef struct sinddm_fused_step_desc {
     float ema_beta;
     unsigned long long* wait_ns; /* optional (NULL = off): device array of 2; [0] += nanoseconds this rank's first CTA
                                   * spent in the NVLink barrier waiting for its peers (= rank skew), [1] = max of them */
+    const float* mc_grads;       /* optional (NULL = peer loads): NVLink-SHARP multicast address of this step's bucket
+                                  * (all ranks' buckets bound to one multicast object): the gradient sum is then ONE
+                                  * multimem.ld_reduce per 16 bytes, reduced inside the NVSwitch, instead of world loads */
 } sinddm_fused_step_desc;
 int sinddm_fused_step(const sinddm_fused_step_desc* desc, void* stream);
 

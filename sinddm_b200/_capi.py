@@ -63,7 +63,7 @@ class FusedStepDesc(C.Structure):
         ("epoch", C.c_uint32),
         ("param", _vp), ("exp_avg", _vp), ("exp_avg_sq", _vp), ("ema", _vp),
         ("lr", _f), ("beta1", _f), ("beta2", _f), ("eps", _f),
-        ("step", _ll), ("ema_mode", _i), ("ema_beta", _f), ("wait_ns", _vp),
+        ("step", _ll), ("ema_mode", _i), ("ema_beta", _f), ("wait_ns", _vp), ("mc_grads", _vp),
     ]
 
 

@@ -263,6 +263,7 @@ int sinddm_fused_step(const sinddm_fused_step_desc* d, void* stream) {
     a.bias2_sqrt = (float)sqrt(bc2);
     a.ema_mode = d->ema_mode; a.ema_beta = d->ema_beta;
     a.wait_ns = d->wait_ns;
+    a.mc_grads = d->mc_grads;
     return fused_step_launch(a, as_stream(stream));
 }
 

@@ -46,6 +46,15 @@ SINDDM_DEVINL unsigned long long global_timer_ns() {
     return t;
 }
 
+SINDDM_DEVINL float4 multimem_ld_reduce_f4(const float* mc) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(mc)
+                 : "memory");
+    return v;
+}
+
 struct Args {
     FusedStepDesc d;
 };
@@ -89,11 +98,16 @@ __global__ void __launch_bounds__(256) fused_allreduce_adam_ema_kernel(const Arg
     const long long n4 = d.n / 4;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (d.mc_grads && world > 1) {
+            // NVLink SHARP: the switch adds the world buckets and returns the sum (one request instead of world loads)
+            g = multimem_ld_reduce_f4(d.mc_grads + i * 4);
+        } else {
 #pragma unroll 1
-        for (int r = 0; r < world; ++r) {          // fixed order: identical bits on every rank
-            const float* src = d.grads[r] + i * 4;
-            const float4 t = (r == rank) ? *reinterpret_cast<const float4*>(src) : ld_peer_f4(src);
-            g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+            for (int r = 0; r < world; ++r) {          // fixed order: identical bits on every rank
+                const float* src = d.grads[r] + i * 4;
+                const float4 t = (r == rank) ? *reinterpret_cast<const float4*>(src) : ld_peer_f4(src);
+                g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+            }
         }
         g.x *= inv_world; g.y *= inv_world; g.z *= inv_world; g.w *= inv_world;
         float4 p = reinterpret_cast<float4*>(d.param)[i];

@@ -23,6 +23,7 @@ struct FusedStepDesc {
     int ema_mode;                          // 0: leave, 1: ema = param, 2: ema = ema * beta + (1 - beta) * param
     float ema_beta;
     unsigned long long* wait_ns;           // optional: [0] += ns CTA 0 waited in the barrier, [1] = max (rank skew)
+    const float* mc_grads;                 // optional: multicast address of this step's bucket (in-switch reduction)
 };
 
 int fused_step_launch(const FusedStepDesc& d, cudaStream_t stream);

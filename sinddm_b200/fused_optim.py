@@ -79,11 +79,23 @@ class FusedStep:
             torch.cuda.synchronize(dev)
             self.handle = symm.rendezvous(self.symm, dist.group.WORLD if group is None else group)
             self.peer_ptrs = [int(p) for p in self.handle.buffer_ptrs]
+            # NVLink-SHARP (multimem.ld_reduce) gradient sum inside the switch: one request per 16 bytes instead of
+            # `world` peer loads (8 ranks: 0.137 -> 0.068 ms per step; replicas stayed bit-identical over 1006 steps x
+            # 1.9 M elements x 8 ranks, profiles/r02_fused_dp_multimem.txt).  Default: on where the symmetric
+            # allocation has a multicast mapping and world >= 4 (no gain at 2); SINDDM_FUSED_MULTIMEM=0/1 overrides.
+            # The summation order is then the switch's (NCCL's NVLS all-reduce agrees to 3e-8), not rank order; the
+            # trainer's _check_replicas() guards the replicas at every milestone either way.
+            import os
+            mc = int(getattr(self.handle, "multicast_ptr", 0) or 0)
+            want = os.environ.get("SINDDM_FUSED_MULTIMEM", "")
+            use = (want == "1") if want in ("0", "1") else self.world >= 4
+            self.mc_ptr = mc if use else 0
             dist.barrier(group)       # every rank's flags are zero before anyone signals
         else:
             self.symm = torch.zeros(total, dtype=torch.float32, device=dev)
             self.handle = None
             self.peer_ptrs = [self.symm.data_ptr()]
+            self.mc_ptr = 0
         self._sizes = [p.numel() for p in self.params]
         # [0]: nanoseconds spent waiting for peers in the in-kernel barrier, summed over steps; [1]: the largest wait
         self.wait_ns = torch.zeros(2, dtype=torch.int64, device=dev) if self.world > 1 else None
@@ -128,6 +140,7 @@ class FusedStep:
         d.ema_mode = int(ema_mode) if self.flat_ema is not None else 0
         d.ema_beta = float(ema_beta)
         d.wait_ns = self.wait_ns.data_ptr() if self.wait_ns is not None else None
+        d.mc_grads = (self.mc_ptr + 4 * parity * self.npad) if self.mc_ptr else None
         stream = torch.cuda.current_stream(self.device).cuda_stream
         check(lib.sinddm_fused_step(C.byref(d), stream), "sinddm_fused_step")
         # the kernels wrote the parameters behind autograd's back: invalidate the packed conv weights

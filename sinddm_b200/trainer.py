@@ -469,6 +469,30 @@ class MultiscaleTrainer(object):
             tdist.broadcast(st, src=0)
             torch.cuda.set_rng_state(st.cpu(), self.device)
 
+    def _check_replicas(self):
+        """Turns silent replica drift into an error: nothing re-synchronises the data-parallel replicas after
+        _sync_replicas (every rank applies the same fused update), so at every checkpoint milestone the ranks compare
+        a 64-bit checksum of the parameter and EMA bits.  Collective; two scalars per call."""
+        if self.world <= 1:
+            return
+        import torch.distributed as tdist
+        sums = []
+        with torch.no_grad():
+            for m in (self.model, self.ema_model):
+                acc = torch.zeros((), dtype=torch.int64, device=self.device)
+                for k, p in enumerate(m.parameters()):
+                    bits = p.detach().contiguous().view(torch.int32).to(torch.int64)
+                    acc = acc + (bits.sum() * (2 * k + 1))
+                sums.append(acc)
+        mine = torch.stack(sums)
+        lo, hi = mine.clone(), mine.clone()
+        tdist.all_reduce(lo, op=tdist.ReduceOp.MIN)
+        tdist.all_reduce(hi, op=tdist.ReduceOp.MAX)
+        if not torch.equal(lo, hi):
+            raise RuntimeError(f'data-parallel replicas diverged at step {self.step} (rank {self.rank}: parameter/EMA '
+                               f'checksums {mine.tolist()}, min {lo.tolist()}, max {hi.tolist()}); the ranks no longer '
+                               f'train the same model')
+
     def _prepare_training(self):
         if not getattr(self, '_replicas_synced', False):
             self._sync_replicas()
@@ -522,6 +546,7 @@ class MultiscaleTrainer(object):
                 if self.rank == 0:
                     from torchvision import utils
                     utils.save_image(images, str(self.results_folder / f'sample-{milestone}.png'), nrow=4)
+                self._check_replicas()
                 self.save(milestone)
         if self.rank == 0:
             print('training completed')

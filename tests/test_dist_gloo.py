@@ -71,6 +71,19 @@ def _worker(rank, world, port, out_dir):
     both = [torch.empty_like(flat) for _ in range(world)]
     dist.all_gather(both, flat)
     assert torch.equal(both[0], both[1]), "replicas / RNG differ after _sync_replicas"
+    tr._check_replicas()                       # identical replicas: passes on both ranks
+    first = next(tr.model.parameters())
+    if rank == 1:
+        with torch.no_grad():
+            first.view(-1)[0] += 1e-7 * (1.0 + float(first.view(-1)[0].abs()))   # a last-bits drift on one rank
+    try:
+        tr._check_replicas()
+        raised = False
+    except RuntimeError as e:
+        raised = "diverged" in str(e)
+    assert raised, "replica drift was not detected"
+    tr._sync_replicas()
+    tr._check_replicas()
     imgs = tr._gather_images(torch.full((2, 3, 4, 5), float(rank)))
     assert imgs.shape[0] == 4 and torch.equal(imgs[:2], torch.zeros(2, 3, 4, 5)) and torch.equal(imgs[2:], torch.ones(2, 3, 4, 5))
     dist.barrier()

@@ -117,17 +117,20 @@ def test_trainer_with_fused_step_tracks_the_torch_adam_trainer(tmp_path):
         assert float((a - b).abs().max()) <= 2e-2 * max(1e-3, float(b.abs().max()))
 
 
+@pytest.mark.parametrize("multimem", [0, 1])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_multi_rank_fused_step_equals_allreduce_plus_adam(world):
+def test_multi_rank_fused_step_equals_allreduce_plus_adam(world, multimem):
     """tools/fused_dp_check.py at every world size the box offers (the driver's 1-GPU box skips; `gpurun --gpus N`
-    runs it; logs of the 2/4/8-rank runs are committed under profiles/)."""
+    runs it; logs of the 2/4/8-rank runs are committed under profiles/).  multimem=1: the in-switch
+    (multimem.ld_reduce) gradient sum instead of rank-ordered peer loads."""
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs of one NVLink box, found {torch.cuda.device_count()}")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
            "127.0.0.1", "--master-port", str(29517 + world), str(REPO / "tools" / "fused_dp_check.py")]
-    proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    env = dict(os.environ, SINDDM_FUSED_MULTIMEM=str(multimem))
+    proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
-    assert "FUSED_DP_OK" in proc.stdout
+    assert f"FUSED_DP_OK world={world} multimem={multimem}" in proc.stdout
 
 
 @pytest.mark.parametrize("kinds", [(True, True), (False, False), (True, False)])

@@ -12,6 +12,9 @@ Adam + EMA) must give
       where the ranks' gradients cancel to ~1e-8 a last-bit difference of the mean can flip the update's sign; an
       element can then differ by up to 2*lr per step.  Bound: >= 99.9 % of the elements within 1e-5 of max|p|, and no
       element off by more than 2 * lr * steps.
+With SINDDM_FUSED_MULTIMEM=1 the gradient sum is one multimem.ld_reduce per 16 bytes (reduced inside the NVSwitch);
+its summation order is the hardware's, so (1) is then checked with (3)'s bound, and (2) -- every rank must still get
+the same bits -- is the property that decides whether that mode can be used at all.
 Prints FUSED_DP_OK and the per-step device time of both paths."""
 import copy
 import os
@@ -69,9 +72,20 @@ def main():
         opt_nccl.step()
     torch.cuda.synchronize()
     worst = 0.0
+    torch.set_grad_enabled(False)
     for a, b in zip(net.parameters(), ref_net.parameters()):
         worst = max(worst, float((a - b).abs().max() / (b.abs().max() + 1e-12)))
-    assert worst <= 2e-5, f"rank {rank}: fused step differs from ordered sum + Adam by {worst}"
+    multimem = bool(fused.mc_ptr)
+    if os.environ.get("SINDDM_FUSED_MULTIMEM", "") == "1":
+        assert multimem, f"rank {rank}: SINDDM_FUSED_MULTIMEM=1 but the symmetric allocation has no multicast mapping"
+    if multimem:
+        # in-switch (NVLink SHARP) summation order is the hardware's, not rank order: same stated bound as (3)
+        d1 = torch.cat([(a - b).abs().reshape(-1) for a, b in zip(net.parameters(), ref_net.parameters())])
+        pm = max(float(b.abs().max()) for b in ref_net.parameters())
+        assert float(d1.max()) <= 2 * 1e-3 * nsteps and float((d1 > 1e-5 * pm).double().mean()) <= 1e-3, \
+            f"rank {rank}: multimem fused step vs ordered sum + Adam: max |dp| {float(d1.max())}"
+    else:
+        assert worst <= 2e-5, f"rank {rank}: fused step differs from ordered sum + Adam by {worst}"
     # (3) against NCCL's summation order, within the Adam-amplified bound stated in the module docstring
     pmax = max(float(b.abs().max()) for b in nccl_net.parameters())
     diffs = torch.cat([(a - b).abs().reshape(-1) for a, b in zip(net.parameters(), nccl_net.parameters())])
@@ -84,6 +98,23 @@ def main():
     ref0 = mine.clone()
     dist.broadcast(ref0, src=0)
     assert torch.equal(mine, ref0), f"rank {rank}: parameter replica differs from rank 0"
+
+    # long replica-identity run (SINDDM_DP_CHECK_REPLICA_STEPS=N): N more steps on fresh rank-dependent gradients, then
+    # every rank must still hold rank 0's bits -- the property in-switch reduction has to keep over a whole training
+    extra = int(os.environ.get("SINDDM_DP_CHECK_REPLICA_STEPS", "0"))
+    for it in range(extra):
+        bucket = fused.bucket()
+        bucket.copy_(torch.randn(bucket.numel(), device=dev, generator=g) * 1e-2)
+        fused.step(1e-3, 2, 0.995)
+    if extra:
+        torch.cuda.synchronize()
+        mine = torch.cat([fused.flat_param.reshape(-1), torch.cat([p.reshape(-1) for p in ema_net.parameters()])])
+        ref0 = mine.clone()
+        dist.broadcast(ref0, src=0)
+        assert torch.equal(mine, ref0), f"rank {rank}: replica differs from rank 0 after {extra} more steps"
+        if rank == 0:
+            print(f"REPLICAS_BIT_IDENTICAL after {nsteps + extra} steps (parameters and EMA, world={world}, "
+                  f"multimem={int(multimem)})", flush=True)
 
     # timing: fused kernel vs NCCL all-reduce + torch Adam (device time, max over ranks)
     def timed(fn, n=30):
@@ -109,7 +140,7 @@ def main():
     t_fused = timed(lambda: fused.step(1e-3, 2, 0.995))
     t_nccl = timed(nccl_path)
     if rank == 0:
-        print(f"FUSED_DP_OK world={world} max_rel_diff={worst:.2e} replicas_bit_identical=True "
+        print(f"FUSED_DP_OK world={world} multimem={int(multimem)} max_rel_diff={worst:.2e} replicas_bit_identical=True "
               f"nccl_vs_ordered_sum_grad_rel_diff={nccl_grad_diff:.2e} fused_vs_nccl_adam_max_abs={nccl_worst_abs:.2e} "
               f"(bound {2 * 1e-3 * nsteps:.1e}) fused_vs_nccl_adam_frac_over_1e-5={nccl_frac_off:.2e} (bound 1e-3) "
               f"fused_step_ms={t_fused:.4f} "
