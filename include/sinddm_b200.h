@@ -15,7 +15,10 @@
  *   - 3-channel image tensors are NCHW fp32 like the reference's; internal activations are NHWC fp32;
  *   - `math`: SINDDM_MATH_TF32 runs the dense 3x3/1x1 convolutions on the tcgen05 tensor cores with TF32
  *     operands and fp32 accumulation (the numerics class of the reference's own GPU default,
- *     torch.backends.cudnn.allow_tf32 = True); SINDDM_MATH_FP32 runs them on CUDA cores in plain fp32.
+ *     torch.backends.cudnn.allow_tf32 = True); SINDDM_MATH_FP32 runs them on CUDA cores in plain fp32;
+ *     SINDDM_MATH_TF32X3 (plans only) runs them on the same tensor-core kernels with every operand split into
+ *     two TF32 values (x = hi + lo): each contraction accumulates x_hi*w_hi + x_hi*w_lo + x_lo*w_hi in fp32, i.e.
+ *     fp32-class results (the reference with allow_tf32 = False) at three times the tensor-core work.
  */
 #ifndef SINDDM_B200_H_
 #define SINDDM_B200_H_
@@ -37,7 +40,7 @@ typedef enum sinddm_status {
     SINDDM_STATUS_WORKSPACE = -4
 } sinddm_status;
 
-enum { SINDDM_MATH_FP32 = 0, SINDDM_MATH_TF32 = 1 };
+enum { SINDDM_MATH_FP32 = 0, SINDDM_MATH_TF32 = 1, SINDDM_MATH_TF32X3 = 2 };
 
 /* Number of parameter tensors of SinDDMNet(multiscale=True), in state_dict / .parameters() order
  * (SinDDM/models.py:104-132, :54-67): time_mlp.{0,2}.{weight,bias}; for l1..l4: mlp.1.{w,b},
@@ -122,9 +125,23 @@ typedef struct sinddm_conv_desc {
 int sinddm_conv_forward(const sinddm_conv_desc* desc, int math, void* stream);
 
 /* PyTorch OIHW weight [Cout][Cin][ntaps] -> forward operand dst_fwd[tap][Cout][Cin] and/or data-gradient
- * operand dst_dgrad[tap][Cin][Cout] (taps flipped). Either destination may be NULL. */
+ * operand dst_dgrad[tap][Cin][Cout] (taps flipped). Either destination may be NULL.
+ * round_tf32: 0 = as is, 1 = rounded to TF32, 2 = the 3xTF32 split: the contraction axis is tripled as
+ * [lo | hi | hi] (dst_fwd[tap][Cout][3*Cin], dst_dgrad[tap][Cin][3*Cout]) to meet activations split by
+ * sinddm_split3(mode 0). */
 int sinddm_pack_conv_weights(const float* w, int Cout, int Cin, int ntaps, float* dst_fwd, float* dst_dgrad,
                              int round_tf32, void* stream);
+
+/* 3xTF32 operand split of x [P][C] (C % 4 == 0): hi = tf32(x) (round to nearest), lo = tf32(x - hi).
+ * mode 0: out [P][3*C] = [hi | lo | hi]   (operand of sinddm_conv_forward with Cin = 3*C and split weights);
+ * mode 1: out [3][P][C] = hi, lo, hi      (x operand of sinddm_conv_wgrad with B tripled);
+ * mode 2: out [3][P][C] = lo, hi, hi      (dy operand of the same call).
+ * The two cross terms come first along the contraction axis and hi*hi last: the tensor core truncates its fp32
+ * accumulator at every MMA step, in proportion to what the accumulator holds at that step.
+ * With SINDDM_MATH_TF32 those calls then return x_hi*w_lo + x_lo*w_hi + x_hi*w_hi accumulated in fp32: what a
+ * SINDDM_MATH_TF32X3 plan does for every dense convolution of SinDDMNet (models.py:62-67,79-80 with
+ * torch.backends.cudnn.allow_tf32 = False). */
+int sinddm_split3(const float* x, long long P, int C, float* out, int mode, void* stream);
 
 /* dW[Cy][Cx][ntaps] = sum_p x[p(+)tap][ci] * dy[p][co] (PyTorch weight-gradient layout).
  * Replaces cuDNN backward-filter for the same modules.  workspace: sinddm_conv_wgrad_workspace_bytes(). */

@@ -65,7 +65,7 @@ def build_parser():
     ap.add_argument("--omega", default=0, type=float)
     ap.add_argument("--loss_factor", default=1, type=float)
     # new: numerics of the dense convolutions (tf32 tensor cores | fp32 CUDA cores)
-    ap.add_argument("--math", default=None, choices=["tf32", "fp32"])
+    ap.add_argument("--math", default=None, choices=["tf32", "tf32x3", "fp32"])
     # new: keep the pyramid in memory instead of writing scale_i/ and scale_i_recon/ next to the image
     ap.add_argument("--in_memory_pyramid", action="store_true")
     return ap

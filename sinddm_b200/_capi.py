@@ -14,6 +14,7 @@ LIB_PATH = PKG_DIR / "lib" / "libsinddm_b200.so"
 
 MATH_FP32 = 0
 MATH_TF32 = 1
+MATH_TF32X3 = 2
 NUM_PARAMS = 52
 
 _vp = C.c_void_p
@@ -83,6 +84,7 @@ SIGNATURES = {
     "sinddm_net_backward": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "sinddm_conv_forward": (_i, [C.POINTER(ConvDesc), _i, _vp]),
     "sinddm_pack_conv_weights": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp]),
+    "sinddm_split3": (_i, [_vp, _ll, _i, _vp, _i, _vp]),
     "sinddm_conv_wgrad_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
     "sinddm_conv_wgrad": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _sz, _i, _vp]),
     "sinddm_dw5x5": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),

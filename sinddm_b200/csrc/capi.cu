@@ -98,7 +98,8 @@ int sinddm_conv_forward(const sinddm_conv_desc* d, int math, void* stream) {
         SINDDM_TRY(tc_conv_prepare(p, &op));
         return tc_conv_launch(op, as_stream(stream));
     }
-    SINDDM_REQUIRE(math == MATH_FP32, "conv_forward: unknown math mode %d", math);
+    SINDDM_REQUIRE(math == MATH_FP32, "conv_forward: math mode %d unknown here (SINDDM_MATH_TF32X3 is a plan mode: "
+                   "single operators get it from sinddm_split3 + split-packed weights under SINDDM_MATH_TF32)", math);
     return simt_conv_launch(p, as_stream(stream));
 }
 
@@ -106,7 +107,13 @@ int sinddm_pack_conv_weights(const float* w, int Cout, int Cin, int ntaps, float
                              int round_tf32, void* stream) {
     SINDDM_REQUIRE(w && (dst_fwd || dst_dgrad), "pack_conv_weights: NULL argument");
     SINDDM_REQUIRE(Cout >= 1 && Cin >= 1 && (ntaps == 9 || ntaps == 1), "pack_conv_weights: bad shape");
+    SINDDM_REQUIRE(round_tf32 >= 0 && round_tf32 <= 2, "pack_conv_weights: round_tf32=%d unknown", round_tf32);
     return pack_conv_weights_launch(w, Cout, Cin, ntaps, dst_fwd, dst_dgrad, round_tf32, as_stream(stream));
+}
+
+int sinddm_split3(const float* x, long long P, int C, float* out, int mode, void* stream) {
+    SINDDM_REQUIRE(x && out && P >= 1 && C >= 4, "split3: bad argument");
+    return split3_launch(x, P, C, out, mode, as_stream(stream));
 }
 
 static int wgrad_nsplit_for(int B, int H, int W, int Cx, int Cy, int ntaps, int math) {

@@ -41,7 +41,7 @@ inline void block_channels(int l, int dim, int channels, int* ci, int* co) {
 inline int max_i(int a, int b) { return a > b ? a : b; }
 
 bool use_tc_conv(int math, int Cin, int Cres, bool has_res_slices, int N) {
-    if (math != MATH_TF32) return false;
+    if (math == MATH_FP32) return false;
     ConvProblem p;
     memset(&p, 0, sizeof(p));
     p.Cin = Cin;
@@ -55,7 +55,7 @@ bool use_tc_conv(int math, int Cin, int Cres, bool has_res_slices, int N) {
 // Rows of the first-conv data-gradient operand: a 3-channel result (l1) runs on the tensor cores with N padded to 16
 // zero weight rows (3 of 16 accumulator columns are stored) instead of a CUDA-core kernel.
 inline int d1_rows(int math, int Ci, int Co) {
-    return (Ci < 16 && use_tc_conv(math, Co, 0, false, 16)) ? 16 : Ci;
+    return (math == MATH_TF32 && Ci < 16 && use_tc_conv(math, Co, 0, false, 16)) ? 16 : Ci;
 }
 
 // l1.net[0] as a 1x1 GEMM over im2col rows (27 patch values padded to one 32-channel chunk)
@@ -68,10 +68,13 @@ inline bool use_im2col(int math, int Ci, int Co) {
     return math == MATH_TF32 && Ci == 3 && tc_conv_supported(p) && tc_wgrad_supported(32, Co);
 }
 
-bool use_tc_wgrad(int math, int Cx, int Cy) { return math == MATH_TF32 && tc_wgrad_supported(Cx, Cy); }
+bool use_tc_wgrad(int math, int Cx, int Cy) { return math != MATH_FP32 && tc_wgrad_supported(Cx, Cy); }
+
+// MATH_TF32X3 runs a tensor-core weight gradient over the batch-tripled split operands
+inline int km(int math) { return math == MATH_TF32X3 ? 3 : 1; }
 
 int wgrad_nsplit(int math, int B, int H, int W, int Cx, int Cy, int ntaps) {
-    return use_tc_wgrad(math, Cx, Cy) ? tc_wgrad_nsplit(B, H, W, Cx, Cy, ntaps)
+    return use_tc_wgrad(math, Cx, Cy) ? tc_wgrad_nsplit(km(math) * B, H, W, Cx, Cy, ntaps)
                                       : simt_wgrad_nsplit(B, H, W, Cx, Cy, ntaps);
 }
 
@@ -104,12 +107,13 @@ size_t carve(Plan* pl, uint8_t* base) {
         block_channels(l, dim, ch, &b.Ci, &b.Co);
         b.has_res = b.Ci != b.Co;
         // packed weights (sized for the blocked layout: K padded to a multiple of 32)
-        b.w0_f = cv.take(packed_weight_floats(9, b.Co, b.Ci));
-        b.w2_f = cv.take(packed_weight_floats(9, b.Co, b.Co));
-        b.wr_f = b.has_res ? cv.take(packed_weight_floats(1, b.Co, b.Ci)) : nullptr;
-        b.w0_d = tr ? cv.take(packed_weight_floats(9, d1_rows(pl->math, b.Ci, b.Co), b.Co)) : nullptr;
-        b.w2_d = tr ? cv.take(packed_weight_floats(9, b.Co, b.Co)) : nullptr;
-        b.wr_d = (tr && b.has_res) ? cv.take(packed_weight_floats(1, b.Ci, b.Co)) : nullptr;
+        const int k3 = km(pl->math);      // MATH_TF32X3 packs [lo | hi | hi] along K
+        b.w0_f = cv.take(packed_weight_floats(9, b.Co, k3 * b.Ci));
+        b.w2_f = cv.take(packed_weight_floats(9, b.Co, k3 * b.Co));
+        b.wr_f = b.has_res ? cv.take(packed_weight_floats(1, b.Co, k3 * b.Ci)) : nullptr;
+        b.w0_d = tr ? cv.take(packed_weight_floats(9, d1_rows(pl->math, b.Ci, b.Co), k3 * b.Co)) : nullptr;
+        b.w2_d = tr ? cv.take(packed_weight_floats(9, b.Co, k3 * b.Co)) : nullptr;
+        b.wr_d = (tr && b.has_res) ? cv.take(packed_weight_floats(1, b.Ci, k3 * b.Co)) : nullptr;
         b.bias2c = b.has_res ? cv.take((size_t)b.Co) : nullptr;
         b.im2col = use_im2col(pl->math, b.Ci, b.Co);
         b.x27 = b.im2col ? cv.take(P * 32) : nullptr;
@@ -137,6 +141,10 @@ size_t carve(Plan* pl, uint8_t* base) {
             if (n0 > partial_max) partial_max = n0;
             if (nr > partial_max) partial_max = nr;
         }
+    }
+    if (pl->math == MATH_TF32X3) {
+        pl->split_a = cv.take(3 * P * dim);
+        pl->split_b = cv.take(3 * P * dim);
     }
     if (tr) {
         pl->dcond_all = cv.take((size_t)B * csum);
@@ -211,7 +219,7 @@ int plan_build(Plan* pl, int B, int H, int W, int dim, int channels, int math, i
     SINDDM_REQUIRE(B >= 1 && H >= 1 && W >= 1, "plan: bad shape B=%d H=%d W=%d", B, H, W);
     SINDDM_REQUIRE(dim >= 2 && dim % 2 == 0 && dim <= 256, "plan: dim=%d unsupported", dim);
     SINDDM_REQUIRE(channels == 3, "plan: channels=%d unsupported (the reference always uses 3)", channels);
-    SINDDM_REQUIRE(math == MATH_FP32 || math == MATH_TF32, "plan: math mode %d unknown", math);
+    SINDDM_REQUIRE(math == MATH_FP32 || math == MATH_TF32 || math == MATH_TF32X3, "plan: math mode %d unknown", math);
     SINDDM_REQUIRE(B <= 65535, "plan: batch too large");
     memset(pl, 0, sizeof(*pl));
     pl->B = B;
@@ -234,20 +242,36 @@ int plan_build(Plan* pl, int B, int H, int W, int dim, int channels, int math, i
     // blocked weight boxes are padded to 32 channels: the padding must read as zero, so clear the packed-weight
     // buffers once (the pack kernels only ever write real elements)
     const char* e2sm = getenv("SINDDM_TC_2SM");
-    pl->blocked_weights = (math == MATH_TF32) && !(e2sm && atoi(e2sm) != 0);
+    pl->blocked_weights = (math != MATH_FP32) && !(e2sm && atoi(e2sm) != 0);
+    const int k3 = km(math);
     for (int l = 0; l < kNumBlocks; ++l) {
         BlockBufs& b = pl->blk[l];
-        SINDDM_CUDA_OK(cudaMemset(b.w0_f, 0, packed_weight_floats(9, b.Co, b.Ci) * sizeof(float)));
-        SINDDM_CUDA_OK(cudaMemset(b.w2_f, 0, packed_weight_floats(9, b.Co, b.Co) * sizeof(float)));
-        if (b.wr_f) SINDDM_CUDA_OK(cudaMemset(b.wr_f, 0, packed_weight_floats(1, b.Co, b.Ci) * sizeof(float)));
+        SINDDM_CUDA_OK(cudaMemset(b.w0_f, 0, packed_weight_floats(9, b.Co, k3 * b.Ci) * sizeof(float)));
+        SINDDM_CUDA_OK(cudaMemset(b.w2_f, 0, packed_weight_floats(9, b.Co, k3 * b.Co) * sizeof(float)));
+        if (b.wr_f) SINDDM_CUDA_OK(cudaMemset(b.wr_f, 0, packed_weight_floats(1, b.Co, k3 * b.Ci) * sizeof(float)));
         if (b.w0_d)
-            SINDDM_CUDA_OK(cudaMemset(b.w0_d, 0, packed_weight_floats(9, d1_rows(math, b.Ci, b.Co), b.Co) * sizeof(float)));
-        if (b.w2_d) SINDDM_CUDA_OK(cudaMemset(b.w2_d, 0, packed_weight_floats(9, b.Co, b.Co) * sizeof(float)));
-        if (b.wr_d) SINDDM_CUDA_OK(cudaMemset(b.wr_d, 0, packed_weight_floats(1, b.Ci, b.Co) * sizeof(float)));
+            SINDDM_CUDA_OK(cudaMemset(b.w0_d, 0, packed_weight_floats(9, d1_rows(math, b.Ci, b.Co), k3 * b.Co) * sizeof(float)));
+        if (b.w2_d) SINDDM_CUDA_OK(cudaMemset(b.w2_d, 0, packed_weight_floats(9, b.Co, k3 * b.Co) * sizeof(float)));
+        if (b.wr_d) SINDDM_CUDA_OK(cudaMemset(b.wr_d, 0, packed_weight_floats(1, b.Ci, k3 * b.Co) * sizeof(float)));
     }
 
     const bool tr = training != 0;
     const int rnd = math == MATH_TF32 ? 1 : 0;
+    const bool x3 = math == MATH_TF32X3;
+    // MATH_TF32X3: a tensor-core problem reads the split copy of its operand (three times the channels, or for the
+    // weight gradients three times the batch); the launch sites in net_forward / net_backward fill split_a / split_b
+    auto conv_x3 = [&](bool tc, ConvProblem& p) {
+        if (!(x3 && tc)) return;
+        p.in = pl->split_a;
+        p.Cin *= 3;
+        if (p.in_res) { p.in_res = pl->split_b; p.Cres *= 3; }
+    };
+    auto wgrad_x3 = [&](bool tc, WgradProblem& p) {
+        if (!(x3 && tc)) return;
+        p.x = pl->split_a;
+        p.dy = pl->split_b;
+        p.B *= 3;
+    };
     const float* prev_o = pl->x_nhwc;
     for (int l = 0; l < kNumBlocks; ++l) {
         BlockBufs& b = pl->blk[l];
@@ -267,6 +291,7 @@ int plan_build(Plan* pl, int B, int H, int W, int dim, int channels, int math, i
         c1.ep.gelu = 1; c1.ep.out = b.a1; c1.ep.out_pre = tr ? b.z1 : nullptr; c1.ep.round_tf32 = rnd && b.tc_c2;
         c1.ep.fast_math = rnd;
         c1.w_blocked = b.tc_c1 && pl->blocked_weights;
+        conv_x3(b.tc_c1, c1);
         if (b.tc_c1) SINDDM_TRY(tc_conv_prepare(c1, &b.c1));
 
         // ---- conv2: a1 -> o, + residual; l4 also carries the final 1x1 conv
@@ -279,6 +304,7 @@ int plan_build(Plan* pl, int B, int H, int W, int dim, int channels, int math, i
         if (!b.has_res) c2.ep.res_add = b.in;
         c2.ep.out = (l < 3 || tr) ? b.o : nullptr;
         c2.w_blocked = b.tc_c2 && pl->blocked_weights;
+        conv_x3(b.tc_c2, c2);
         if (b.tc_c2) SINDDM_TRY(tc_conv_prepare(c2, &b.c2));
 
         if (tr) {
@@ -353,6 +379,12 @@ int plan_build(Plan* pl, int B, int H, int W, int dim, int channels, int math, i
                 const char* e = getenv("SINDDM_TC_COLSUM");    // A/B switch; default on
                 if (b.tc_d2 && !(e && atoi(e) == 0)) b.pd2.ep.colsum_part = pl->colsum_scratch;
             }
+            conv_x3(b.tc_d2, b.pd2);
+            conv_x3(b.tc_d1, b.pd1);
+            conv_x3(b.tc_dr, b.pdr);
+            wgrad_x3(b.tc_w2, b.pw2);
+            wgrad_x3(b.tc_w0, b.pw0);
+            wgrad_x3(b.tc_wr, b.pwr);
             if (b.tc_d2) SINDDM_TRY(tc_conv_prepare(b.pd2, &b.d2));
             if (b.tc_d1) SINDDM_TRY(tc_conv_prepare(b.pd1, &b.d1));
             if (b.tc_dr) SINDDM_TRY(tc_conv_prepare(b.pdr, &b.dr));
@@ -377,7 +409,8 @@ int plan_build(Plan* pl, int B, int H, int W, int dim, int channels, int math, i
 }
 
 int net_pack_weights(Plan* pl, const float* const* params, cudaStream_t s) {
-    const int rnd = pl->math == MATH_TF32 ? 1 : 0;
+    // tensor-core layers: 1 = round to tf32, 2 = MATH_TF32X3's [lo | hi | hi] split along K; CUDA-core layers: 0
+    const int rnd = pl->math == MATH_TF32 ? 1 : (pl->math == MATH_TF32X3 ? 2 : 0);
     struct PdlScope {
         explicit PdlScope(long long px) { pdl_set(px <= pdl_max_pixels()); }
         ~PdlScope() { pdl_set(false); }
@@ -391,23 +424,23 @@ int net_pack_weights(Plan* pl, const float* const* params, cudaStream_t s) {
         if (b.im2col) {
             pack_jobs_add_im2col(&jobs, params[b.pbase + 6], b.Co, b.w0_f, rnd, pl->blocked_weights);
             if (pl->training)
-                pack_jobs_add_conv(&jobs, params[b.pbase + 6], b.Co, b.Ci, 9, nullptr, b.w0_d, rnd && b.tc_d1,
+                pack_jobs_add_conv(&jobs, params[b.pbase + 6], b.Co, b.Ci, 9, nullptr, b.w0_d, b.tc_d1 ? rnd : 0,
                                    b.tc_d1 && pl->blocked_weights, b.pd1.N);
         } else if (pl->training && b.tc_d1 != b.tc_c1) {
             // l1: the forward conv (Cin = 3) runs on CUDA cores, its data gradient on the tensor cores
-            pack_jobs_add_conv(&jobs, params[b.pbase + 6], b.Co, b.Ci, 9, b.w0_f, nullptr, rnd && b.tc_c1,
+            pack_jobs_add_conv(&jobs, params[b.pbase + 6], b.Co, b.Ci, 9, b.w0_f, nullptr, b.tc_c1 ? rnd : 0,
                                b.tc_c1 && pl->blocked_weights);
-            pack_jobs_add_conv(&jobs, params[b.pbase + 6], b.Co, b.Ci, 9, nullptr, b.w0_d, rnd && b.tc_d1,
+            pack_jobs_add_conv(&jobs, params[b.pbase + 6], b.Co, b.Ci, 9, nullptr, b.w0_d, b.tc_d1 ? rnd : 0,
                                b.tc_d1 && pl->blocked_weights, b.pd1.N);
         } else {
-            pack_jobs_add_conv(&jobs, params[b.pbase + 6], b.Co, b.Ci, 9, b.w0_f, b.w0_d, rnd && b.tc_c1,
+            pack_jobs_add_conv(&jobs, params[b.pbase + 6], b.Co, b.Ci, 9, b.w0_f, b.w0_d, b.tc_c1 ? rnd : 0,
                                b.tc_c1 && pl->blocked_weights, pl->training ? b.pd1.N : 0);
         }
-        pack_jobs_add_conv(&jobs, params[b.pbase + 8], b.Co, b.Co, 9, b.w2_f, b.w2_d, rnd && b.tc_c2,
+        pack_jobs_add_conv(&jobs, params[b.pbase + 8], b.Co, b.Co, 9, b.w2_f, b.w2_d, b.tc_c2 ? rnd : 0,
                            b.tc_c2 && pl->blocked_weights);
         if (b.has_res) {
             if (b.Ci >= 8)
-                pack_jobs_add_conv(&jobs, params[b.pbase + 10], b.Co, b.Ci, 1, b.wr_f, b.wr_d, rnd && b.tc_c2,
+                pack_jobs_add_conv(&jobs, params[b.pbase + 10], b.Co, b.Ci, 1, b.wr_f, b.wr_d, b.tc_c2 ? rnd : 0,
                                    b.tc_c2 && pl->blocked_weights);
             // net[2].bias + res_conv.bias enter the same epilogue
             pack_jobs_add_sum(&jobs, params[b.pbase + 9], params[b.pbase + 11], b.bias2c, b.Co);
@@ -439,6 +472,7 @@ int net_forward(Plan* pl, const float* const* params, const float* x_nchw, const
                 const float* freqs, float* out_nchw, cudaStream_t s) {
     const int B = pl->B, H = pl->H, W = pl->W;
     const int rnd = pl->math == MATH_TF32 ? 1 : 0;
+    const bool x3 = pl->math == MATH_TF32X3;
     struct PdlScope {   // programmatic dependent launches only where the launch overheads matter (small problems)
         explicit PdlScope(long long px) { pdl_set(px <= pdl_max_pixels()); }
         ~PdlScope() { pdl_set(false); }
@@ -452,10 +486,11 @@ int net_forward(Plan* pl, const float* const* params, const float* x_nchw, const
         BlockBufs& b = pl->blk[l];
         // h0 = ds_conv(x) + bias + cond      (models.py:70-77)
         SINDDM_TRY(dw5x5_launch(b.in, params[b.pbase + 4], params[b.pbase + 5], b.cond, nullptr, b.h0, B, H, W, b.Ci,
-                                0, rnd && b.tc_c1, s));
+                                0, b.tc_c1 ? rnd : 0, s));
         if (b.im2col) SINDDM_TRY(im2col3x3_c3_launch(b.h0, b.x27, B, H, W, 0, s));   // h0 is already tf32-rounded
         // a1 = GELU(net[0](h0))              (models.py:63-64)
         b.pc1.ep.bias = params[b.pbase + 7];
+        if (x3 && b.tc_c1) SINDDM_TRY(split3_launch(b.h0, pl->P, b.Ci, pl->split_a, 0, s));
         SINDDM_TRY(run_conv(b.tc_c1, b.c1, b.pc1, s));
         // o = net[2](a1) + res_conv(x)       (models.py:65,80)
         ConvEpilogue& e2 = b.pc2.ep;
@@ -465,6 +500,10 @@ int net_forward(Plan* pl, const float* const* params, const float* x_nchw, const
             e2.w_final = params[kNumParams - 2];
             e2.b_final = params[kNumParams - 1];
             e2.out_final = out_nchw;
+        }
+        if (x3 && b.tc_c2) {
+            SINDDM_TRY(split3_launch(b.a1, pl->P, b.Co, pl->split_a, 0, s));
+            if (b.pc2.in_res) SINDDM_TRY(split3_launch(b.in, pl->P, b.Ci, pl->split_b, 0, s));
         }
         SINDDM_TRY(run_conv(b.tc_c2, b.c2, b.pc2, s));
     }
@@ -476,10 +515,20 @@ int net_backward(Plan* pl, const float* const* params, const float* dout_nchw, f
     const int B = pl->B, H = pl->H, W = pl->W;
     const long long P = pl->P;
     const int rnd = pl->math == MATH_TF32 ? 1 : 0;
+    const bool x3 = pl->math == MATH_TF32X3;
     struct PdlScope {
         explicit PdlScope(long long px) { pdl_set(px <= pdl_max_pixels()); }
         ~PdlScope() { pdl_set(false); }
     } pdl_scope(P);
+    // MATH_TF32X3: split operands of the next tensor-core launch (conv: channels tripled; wgrad: batch tripled)
+    auto split_conv = [&](bool tc, const float* src, int C) -> int {
+        return (x3 && tc) ? split3_launch(src, P, C, pl->split_a, 0, s) : SINDDM_OK;
+    };
+    auto split_wgrad = [&](bool tc, const float* x, int Cx, const float* dy, int Cy) -> int {
+        if (!(x3 && tc)) return SINDDM_OK;
+        SINDDM_TRY(split3_launch(x, P, Cx, pl->split_a, 1, s));
+        return split3_launch(dy, P, Cy, pl->split_b, 2, s);
+    };
 
     // ---- final_conv: bias / weight gradients and the gradient into l4's output
     SINDDM_TRY(nchw_to_nhwc_launch(dout_nchw, pl->dout_nhwc, B, pl->channels, H, W, s));
@@ -511,21 +560,27 @@ int net_backward(Plan* pl, const float* const* params, const float* dout_nchw, f
                                                cudaMemcpyDeviceToDevice, s));
         }
         // weight gradients of net[2] and res_conv
+        SINDDM_TRY(split_wgrad(b.tc_w2, b.a1, b.Co, d_o, b.Co));
         SINDDM_TRY(run_wgrad(b.tc_w2, b.wg2, b.pw2, grads[b.pbase + 8], s));
         if (b.has_res) {
-            if (!b.tc_wr && b.Ci == 3 && final_conv_bwd_supported(b.Co))   // l1.res_conv: one streaming pass over d_o
+            if (!b.tc_wr && b.Ci == 3 && final_conv_bwd_supported(b.Co)) {  // l1.res_conv: one streaming pass over d_o
                 SINDDM_TRY(wgrad_from_c3_launch(b.in, d_o, P, b.Co, grads[b.pbase + 10], pl->colsum_scratch, s));
-            else
+            } else {
+                SINDDM_TRY(split_wgrad(b.tc_wr, b.in, b.Ci, d_o, b.Co));
                 SINDDM_TRY(run_wgrad(b.tc_wr, b.wgr, b.pwr, grads[b.pbase + 10], s));
+            }
         }
         // dz1 = conv3x3^T(d_o) * gelu'(z1)
+        SINDDM_TRY(split_conv(b.tc_d2, d_o, b.Co));
         SINDDM_TRY(run_conv(b.tc_d2, b.d2, b.pd2, s));
         if (b.tc_d2 && b.pd2.ep.colsum_part)
             SINDDM_TRY(colsum_final_launch(pl->colsum_scratch, tc_conv_colsum_rows(b.d2), b.Co, grads[b.pbase + 7], s));
         else
             SINDDM_TRY(colsum_launch(pl->dz1, P, b.Co, grads[b.pbase + 7], pl->colsum_scratch, s));
+        SINDDM_TRY(split_wgrad(b.tc_w0, b.h0, b.Ci, pl->dz1, b.Co));      // (im2col never coexists with MATH_TF32X3)
         SINDDM_TRY(run_wgrad(b.tc_w0, b.wg0, b.pw0, grads[b.pbase + 6], s, b.im2col ? 2 : 0));
         // dh0 = conv3x3^T(dz1)
+        SINDDM_TRY(split_conv(b.tc_d1, pl->dz1, b.Co));
         SINDDM_TRY(run_conv(b.tc_d1, b.d1, b.pd1, s));
         // depthwise weight / bias / conditioning gradients
         SINDDM_TRY(dw5x5_wgrad_launch(b.in, pl->dh0, grads[b.pbase + 4], grads[b.pbase + 5], b.dcond, pl->dw_scratch,
@@ -534,6 +589,7 @@ int net_backward(Plan* pl, const float* const* params, const float* dout_nchw, f
             // gradient into the block input: depthwise^T(dh0) + residual path
             const float* addp = d_o;
             if (b.has_res) {
+                SINDDM_TRY(split_conv(b.tc_dr, d_o, b.Co));
                 SINDDM_TRY(run_conv(b.tc_dr, b.dr, b.pdr, s));
                 addp = pl->dxres;
             }

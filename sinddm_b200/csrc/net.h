@@ -46,7 +46,10 @@ int cond_fwd_launch(const CondParams& P, const long long* time, float scale, con
 int cond_bwd_launch(const CondParams& P, const CondGrads& G, int B, const CondSaved& S, const float* dcond,
                     float* scratch, cudaStream_t stream);
 
-enum MathMode { MATH_FP32 = 0, MATH_TF32 = 1 };
+// MATH_TF32X3: the tensor-core kernels of MATH_TF32 fed with hi/lo-split operands (x = hi + lo, both tf32): every
+// contraction adds x_hi w_hi + x_hi w_lo + x_lo w_hi into its fp32 accumulator -- fp32-class accuracy at three times
+// the MMA work (the reference's behaviour with torch.backends.cudnn.allow_tf32 = False, on the tensor cores).
+enum MathMode { MATH_FP32 = 0, MATH_TF32 = 1, MATH_TF32X3 = 2 };
 
 struct BlockBufs {
     int Ci, Co;
@@ -83,6 +86,7 @@ struct Plan {
     float *wf_d;                 // final conv data-gradient weights [1][half][3]
     float *dout_nhwc, *d_a, *d_b, *dz1, *dh0, *dxres;
     float *partial, *dw_scratch, *colsum_scratch, *colsum_out;
+    float *split_a, *split_b;    // MATH_TF32X3: the split operands of the next tensor-core launch ([P][3C] or [3P][C])
     BlockBufs blk[kNumBlocks];
     // final conv gradient problems
     ConvProblem pfd;

@@ -149,6 +149,11 @@ void pack_jobs_add_im2col(PackJobs* jobs, const float* w, int Co, float* dst, in
 void pack_jobs_add_sum(PackJobs* jobs, const float* a, const float* b, float* o, int n);
 int pack_jobs_launch(PackJobs* jobs, cudaStream_t stream);
 
+// 3xTF32 operand split (MATH_TF32X3): hi = tf32(x), lo = tf32(x - hi).  mode 0: out [P][3C] = [hi | lo | hi];
+// mode 1: out [3][P][C] = hi, lo, hi;  mode 2: out [3][P][C] = lo, hi, hi.  Weights are packed to match with
+// round == 2 in pack_conv_weights / pack_jobs_add_conv ([lo | hi | hi] along K, K tripled): cross terms first.
+int split3_launch(const float* x, long long P, int C, float* out, int mode, cudaStream_t stream);
+
 // floats needed by a packed weight buffer in either layout ([ntaps][N][K] or blocked with K padded to 32)
 inline size_t packed_weight_floats(int ntaps, int N, int K) { return (size_t)ntaps * N * ((K + 31) / 32 * 32); }
 

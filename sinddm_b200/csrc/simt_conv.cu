@@ -232,9 +232,56 @@ __device__ __forceinline__ void pack_conv_one(int i, const float* __restrict__ w
     const int ci = (i / ntaps) % Cin;
     const int co = i / (ntaps * Cin);
     float v = w[i];
+    if (round == 2) {
+        // 3xTF32 (MATH_TF32X3): K is tripled as [lo | hi | hi], matching activations split as [hi | lo | hi]
+        // (split3_launch), so that one pass over K adds x_hi w_lo + x_lo w_hi + x_hi w_hi into the fp32 accumulator.
+        // The two small cross terms come FIRST: the tensor core truncates its fp32 accumulator at every MMA step (an
+        // error proportional to the accumulator's magnitude at that step), so only the last third of the steps --
+        // the ones that add x_hi w_hi -- still pay it.
+        const float hi = round_tf32(v), lo = round_tf32(v - hi);
+        if (dst_fwd) {
+            dst_fwd[packed_index(tap, co, ci, Cout, 3 * Cin, blocked)] = lo;
+            dst_fwd[packed_index(tap, co, Cin + ci, Cout, 3 * Cin, blocked)] = hi;
+            dst_fwd[packed_index(tap, co, 2 * Cin + ci, Cout, 3 * Cin, blocked)] = hi;
+        }
+        if (dst_dgrad) {
+            dst_dgrad[packed_index(ntaps - 1 - tap, ci, co, dgrad_rows, 3 * Cout, blocked)] = lo;
+            dst_dgrad[packed_index(ntaps - 1 - tap, ci, Cout + co, dgrad_rows, 3 * Cout, blocked)] = hi;
+            dst_dgrad[packed_index(ntaps - 1 - tap, ci, 2 * Cout + co, dgrad_rows, 3 * Cout, blocked)] = hi;
+        }
+        return;
+    }
     if (round) v = round_tf32(v);
     if (dst_fwd) dst_fwd[packed_index(tap, co, ci, Cout, Cin, blocked)] = v;
     if (dst_dgrad) dst_dgrad[packed_index(ntaps - 1 - tap, ci, co, dgrad_rows, Cout, blocked)] = v;
+}
+
+// 3xTF32 operand split: hi = tf32(x) (round to nearest), lo = tf32(x - hi) (x - hi is exact in fp32), so that
+// x = hi + lo up to 2^-22 |x|.  mode 0: out[p][3C] = [hi | lo | hi] (conv operand: channels tripled, meets weights
+// packed [lo | hi | hi]); mode 1: out[3][P][C] = hi, lo, hi (weight-gradient x operand: batch tripled); mode 2:
+// out[3][P][C] = lo, hi, hi (weight-gradient dy operand).  The cross terms hi*lo, lo*hi come first along the
+// contraction axis, hi*hi last (see pack_conv_one).  One float4 per thread; C % 4 == 0.
+__global__ void __launch_bounds__(256)
+split3_kernel(const float4* __restrict__ x, float4* __restrict__ out, long long n4, int C4, int mode) {
+    pdl_grid_sync();   // programmatic dependent launch: nothing above touches global memory
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(x + i);
+        float4 hi, lo;
+        hi.x = round_tf32(v.x); hi.y = round_tf32(v.y); hi.z = round_tf32(v.z); hi.w = round_tf32(v.w);
+        lo.x = round_tf32(v.x - hi.x); lo.y = round_tf32(v.y - hi.y);
+        lo.z = round_tf32(v.z - hi.z); lo.w = round_tf32(v.w - hi.w);
+        if (mode == 0) {
+            const long long p = i / C4;
+            const long long o = p * 3 * C4 + (i - p * C4);
+            out[o] = hi;
+            out[o + C4] = lo;
+            out[o + 2 * C4] = hi;
+        } else {
+            out[i] = mode == 1 ? hi : lo;
+            out[n4 + i] = mode == 1 ? lo : hi;
+            out[2 * n4 + i] = hi;
+        }
+    }
 }
 
 __global__ void __launch_bounds__(256) pack_jobs_kernel(const PackJobs jobs) {
@@ -855,6 +902,17 @@ int pack_conv_weights_launch(const float* w, int Cout, int Cin, int ntaps, float
     const int total = Cout * Cin * ntaps;
     (void)launch_pdl(pack_conv_weights_kernel, dim3(ceil_div(total, 256)), dim3(256), (size_t)(0), stream, w, Cout, Cin, ntaps, dst_fwd, dst_dgrad, round,
                                                                        blocked, dgrad_rows > Cin ? dgrad_rows : Cin);
+    SINDDM_CUDA_OK(cudaGetLastError());
+    return SINDDM_OK;
+}
+
+int split3_launch(const float* x, long long P, int C, float* out, int mode, cudaStream_t stream) {
+    SINDDM_REQUIRE(C % 4 == 0 && mode >= 0 && mode <= 2, "split3: C=%d mode=%d unsupported", C, mode);
+    const long long n4 = P * (C / 4);
+    const long long cap = 32ll * (device_info().initialized ? device_info().num_sms : 148);
+    const long long want = (n4 + 255) / 256;
+    (void)launch_pdl(split3_kernel, dim3((unsigned)(want < cap ? want : cap)), dim3(256), (size_t)0, stream,
+                     reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(out), n4, C / 4, mode);
     SINDDM_CUDA_OK(cudaGetLastError());
     return SINDDM_OK;
 }

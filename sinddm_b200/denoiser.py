@@ -19,14 +19,15 @@ import torch
 from torch import nn
 
 from . import _capi
-from ._capi import MATH_FP32, MATH_TF32, NUM_PARAMS, check
+from ._capi import MATH_FP32, MATH_TF32, MATH_TF32X3, NUM_PARAMS, check
 from .functions import default, exists
 
-_MATH_NAMES = {"fp32": MATH_FP32, "tf32": MATH_TF32}
+_MATH_NAMES = {"fp32": MATH_FP32, "tf32": MATH_TF32, "tf32x3": MATH_TF32X3}
 
 
 def default_math() -> int:
-    """TF32 tensor-core math unless SINDDM_MATH=fp32 (strict CUDA-core fp32 mode)."""
+    """TF32 tensor-core math unless SINDDM_MATH=tf32x3 (fp32-class results on the tensor cores: every operand split
+    into two TF32 values, three MMAs per product) or SINDDM_MATH=fp32 (the CUDA-core twin, a test oracle)."""
     return _MATH_NAMES[os.environ.get("SINDDM_MATH", "tf32").lower()]
 
 

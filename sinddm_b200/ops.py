@@ -56,13 +56,26 @@ def nhwc_to_nchw(x: torch.Tensor) -> torch.Tensor:
 # dense convolution (NHWC) and its gradients
 # ------------------------------------------------------------------------------------------------
 
-def pack_conv_weights(w: torch.Tensor, round_tf32: bool = False):
-    """OIHW weight -> (forward operand [tap][Cout][Cin], data-gradient operand [tap][Cin][Cout])."""
+def split3(x: torch.Tensor, mode: int = 0) -> torch.Tensor:
+    """3xTF32 operand split of an NHWC tensor [B,H,W,C]: mode 0 -> [B,H,W,3C] = [hi | lo | hi] (conv operand),
+    mode 1 -> [3B,H,W,C] = hi, lo, hi (weight-gradient x operand), mode 2 -> [3B,H,W,C] = lo, hi, hi (its dy operand)."""
+    lib = _prep(x)
+    B, H, W, Cc = x.shape
+    shape = (B, H, W, 3 * Cc) if mode == 0 else (3 * B, H, W, Cc)
+    out = torch.empty(shape, dtype=torch.float32, device=x.device)
+    check(lib.sinddm_split3(ptr(x), B * H * W, Cc, ptr(out), int(mode), _stream(x)), "split3")
+    return out
+
+
+def pack_conv_weights(w: torch.Tensor, round_tf32=False):
+    """OIHW weight -> (forward operand [tap][Cout][Cin], data-gradient operand [tap][Cin][Cout]); round_tf32 = 2: the
+    3xTF32 split layouts [tap][Cout][3 Cin] / [tap][Cin][3 Cout] ([lo | hi | hi] along the contraction axis)."""
     lib = _prep(w)
     co, ci, kh, kw = w.shape
     ntaps = kh * kw
-    fwd = torch.empty((ntaps, co, ci), dtype=torch.float32, device=w.device)
-    dgr = torch.empty((ntaps, ci, co), dtype=torch.float32, device=w.device)
+    k3 = 3 if int(round_tf32) == 2 else 1
+    fwd = torch.empty((ntaps, co, k3 * ci), dtype=torch.float32, device=w.device)
+    dgr = torch.empty((ntaps, ci, k3 * co), dtype=torch.float32, device=w.device)
     check(lib.sinddm_pack_conv_weights(ptr(w), co, ci, ntaps, ptr(fwd), ptr(dgr), int(round_tf32), _stream(w)),
           "pack_conv_weights")
     return fwd, dgr
