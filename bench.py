@@ -325,12 +325,12 @@ class Job:
         return float(t.item())
 
 
-def make_trainer(job, sizes, t_ideal, global_batch, tag):
+def make_trainer(job, sizes, t_ideal, global_batch, tag, math=None):
     from sinddm_b200 import MultiScaleGaussianDiffusion, MultiscaleTrainer, SinDDMNet
     tmp = Path(tempfile.mkdtemp(prefix=f"sinddm_bench_{tag}_r{job.rank}_"))
     synthetic_pyramid(tmp, sizes)
     dev = job.dev
-    net = SinDDMNet(dim=DIM, multiscale=True, device=dev).to(dev)
+    net = SinDDMNet(dim=DIM, multiscale=True, device=dev, math=math).to(dev)
     dif = MultiScaleGaussianDiffusion(denoise_fn=net, n_scales=5, scale_factor=1.403, image_sizes=sizes,
                                       timesteps=100, train_full_t=True, scale_losses=BALLOONS_SCALE_LOSSES,
                                       loss_type="l1", reblurring=True, omega=0, device=dev,
@@ -529,6 +529,32 @@ def sampling_leg(job, trainer, t_ideal, global_batch, scale_mul=(1, 1)):
             "d2h": host_imgs.numel() * 4}
 
 
+def strict_mode_leg(job):
+    """The same training step in math = "tf32x3" (3xTF32: every conv operand split into two TF32 values, fp32-class
+    results -- the reference with allow_tf32 = False -- on the same tcgen05 kernels): device ms per step and scale,
+    three timed steps each after two warm ones.  A side record, not the headline (which is the TF32 default both the
+    reference's GPU path and this one use)."""
+    trainer = make_trainer(job, BALLOONS_SIZES, BALLOONS_T_IDEAL, BATCH * job.world, "x3", math="tf32x3")
+    per = []
+    for s in range(len(BALLOONS_SIZES)):
+        for _ in range(2):
+            trainer.train_step(s=s)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            trainer.train_step(s=s)
+        e1.record()
+        torch.cuda.synchronize()
+        per.append(e0.elapsed_time(e1) / 3)
+    del trainer
+    release_memory()
+    return {"math": "tf32x3", "value": 1e3 * len(per) / sum(per), "unit": "steps/s", "per_scale_ms_per_step": per,
+            "note": "3xTF32 on the tensor cores (x = hi + lo; x_hi*w_lo + x_lo*w_hi + x_hi*w_hi accumulated in fp32): "
+                    "per-convolution error 2e-6 .. 4e-6 of max|ref| vs 4e-4 for TF32 (profiles/r02_tf32x3.txt); "
+                    "scales visited round-robin, batch 32"}
+
+
 def release_memory():
     """Call after `del trainer` in the caller's frame: plans, workspaces and cached blocks go back to the driver."""
     gc.collect()
@@ -622,6 +648,13 @@ def run_b200_arm(args):
     smp = sampling_leg(job, trainer, BALLOONS_T_IDEAL, SAMPLE_BATCH * world)
     del trainer
     release_memory()
+    strict = None
+    if world == 1 and not args.no_baselines:
+        try:
+            strict = strict_mode_leg(job)
+        except Exception as e:  # noqa: BLE001 -- a side record must not take the measurement down
+            strict = {"failed": f"{type(e).__name__}: {e}"}
+            release_memory()
 
     others = {}
     if not args.no_other_configs:
@@ -718,6 +751,8 @@ def run_b200_arm(args):
     }
     if others:
         result["other_configs"] = others
+    if strict is not None:
+        result["strict_mode"] = strict
     if eager is not None:
         result["gpu_eager_baseline"] = eager
     if world == 1 and not args.no_baselines:

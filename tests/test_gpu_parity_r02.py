@@ -53,7 +53,10 @@ def stored_errors(g, prefix, named):
     return worst, worst_norm, where
 
 
-@pytest.mark.parametrize("math", ["fp32", "tf32"])
+STRICT = ("fp32", "tf32x3")    # math modes held to fp32-class bounds (tf32x3 = 3xTF32 on the tensor cores)
+
+
+@pytest.mark.parametrize("math", ["fp32", "tf32", "tf32x3"])
 def test_finest_scale_vs_reference_golden(golden, math):
     from oracle import sinddm_oracle as orc
     g = golden("g7_finest_scale.npz")
@@ -84,6 +87,10 @@ def test_finest_scale_vs_reference_golden(golden, math):
           f"worst grad max-err/max {e_grad:.2e} ({where}), worst grad-norm rel {e_gnorm:.2e}")
     if math == "fp32":
         assert e_pred <= 2e-4 and e_norm <= 1e-5 and e_loss <= 1e-5 and e_grad <= 2e-4 and e_gnorm <= 2e-4
+    elif math == "tf32x3":
+        # per-convolution error 2e-6 .. 4e-6 (the tensor core truncates its fp32 accumulator at every MMA step) instead of
+        # the CUDA-core twin's 1e-7: same element-wise bounds, norms / loss within 5e-5
+        assert e_pred <= 2e-4 and e_norm <= 5e-5 and e_loss <= 5e-5 and e_grad <= 2e-4 and e_gnorm <= 2e-4
     else:
         # the L1 gradient is sign(pred - noise)/N: TF32 forward rounding flips a few signs, so the gradient tolerance is
         # the single-evaluation TF32 class
@@ -94,7 +101,7 @@ def forest_state():
     return {k: torch.from_numpy(v) for k, v in np.load(GOLDEN / "forest_ema_state.npz").items()}
 
 
-@pytest.mark.parametrize("math", ["fp32", "tf32"])
+@pytest.mark.parametrize("math", ["fp32", "tf32", "tf32x3"])
 def test_trained_forest_weights_vs_reference_golden(golden, math):
     from sinddm_b200 import ops
     g = golden("g8_forest_weights.npz")
@@ -129,7 +136,7 @@ def test_trained_forest_weights_vs_reference_golden(golden, math):
             err_rel = max_err_rel(eps, ref)
             print(f"G8 {math} s{sc} t{ti}: max abs err {err_abs:.2e} (max|eps| {float(ref.abs().max()):.2f}), "
                   f"rel L2 {rel_err(eps, ref):.2e}, L1 loss {loss.item():.4f} vs {float(g[f's{sc}_t{ti}_loss']):.4f}")
-            if math == "fp32":
+            if math in STRICT:
                 assert err_rel <= 2e-4
                 assert loss.item() == pytest.approx(float(g[f"s{sc}_t{ti}_loss"]), rel=1e-4)
             else:
@@ -141,9 +148,9 @@ def test_trained_forest_weights_vs_reference_golden(golden, math):
     with torch.no_grad():
         y0 = net(xa, ta, 0).cpu()
     print(f"G8 {math} anchor: mean {float(y0.mean()):.6f} std {float(y0.std()):.6f} (reference -0.125442 / 5.028523)")
-    assert float(y0.mean()) == pytest.approx(-0.125442, abs=2e-5 if math == "fp32" else 2e-3)
-    assert float(y0.std()) == pytest.approx(5.028523, abs=2e-4 if math == "fp32" else 5e-3)
-    assert max_err_rel(y0, torch.from_numpy(g["anchor_s0"])) <= (2e-4 if math == "fp32" else 3e-2)
+    assert float(y0.mean()) == pytest.approx(-0.125442, abs=2e-5 if math in STRICT else 2e-3)
+    assert float(y0.std()) == pytest.approx(5.028523, abs=2e-4 if math in STRICT else 5e-3)
+    assert max_err_rel(y0, torch.from_numpy(g["anchor_s0"])) <= (2e-4 if math in STRICT else 3e-2)
 
 
 def test_trainer_load_reads_an_authors_format_checkpoint(tmp_path):
@@ -180,11 +187,11 @@ def test_trainer_load_reads_an_authors_format_checkpoint(tmp_path):
     assert torch.isfinite(out[-1]).all() and float(out[-1].abs().max()) <= 1.0 + 1e-5
 
 
-@pytest.mark.parametrize("fused", ["1", "0"])
-def test_trainer_steps_vs_reference_trainer_golden(golden, monkeypatch, fused):
+@pytest.mark.parametrize("fused,math", [("1", "fp32"), ("0", "fp32"), ("1", "tf32x3")])
+def test_trainer_steps_vs_reference_trainer_golden(golden, monkeypatch, fused, math):
     """a16: four steps of the reference MultiscaleTrainer.train() (G9) replayed through MultiscaleTrainer.train_step in
     math=fp32 -- same scale per step, same t, same noise -- with the fused all-reduce+Adam+EMA kernel and with
-    torch.optim.Adam + the EMA class."""
+    torch.optim.Adam + the EMA class; and in math=tf32x3 (the strict mode a user would actually train in)."""
     from PIL import Image
     from oracle import sinddm_oracle as orc
     from sinddm_b200 import MultiscaleTrainer
@@ -192,7 +199,7 @@ def test_trainer_steps_vs_reference_trainer_golden(golden, monkeypatch, fused):
     g = golden("g9_trainer_steps.npz")
     ns = int(g["n_scales"])
     sizes = [tuple(int(v) for v in row) for row in g["sizes"]]
-    net, dif = build("fp32", sizes, list(g["scale_losses"]), orc.synthetic_params(seed=11, dim=160),
+    net, dif = build(math, sizes, list(g["scale_losses"]), orc.synthetic_params(seed=11, dim=160),
                      scale_factor=float(g["scale_factor"]))
     as_img = lambda u8: Image.fromarray(np.ascontiguousarray(u8.transpose(1, 2, 0)))
     pyr = [(as_img(g[f"data{i}_orig_u8"]), as_img(g[f"data{i}_blur_u8"])) for i in range(ns)]
@@ -212,18 +219,20 @@ def test_trainer_steps_vs_reference_trainer_golden(golden, monkeypatch, fused):
         monkeypatch.setattr(torch, "randint", real_randint)
     assert tr.step == int(g["step_final"])
     assert tr.scheduler.get_last_lr()[0] == pytest.approx(float(g["lr_final"]))
-    np.testing.assert_allclose(tr.running_loss, g["running_loss"], rtol=2e-5)
+    np.testing.assert_allclose(tr.running_loss, g["running_loss"], rtol=2e-5 if math == "fp32" else 1e-4)
     e_m, n_m, w_m = stored_errors(g, "model", tr.model.denoise_fn.named_parameters())
     e_e, n_e, w_e = stored_errors(g, "ema", tr.ema_model.denoise_fn.named_parameters())
-    print(f"G9 fused={fused}: model worst max-err/max {e_m:.2e} ({w_m}), norm rel {n_m:.2e}; ema {e_e:.2e} ({w_e}), "
+    print(f"G9 fused={fused} {math}: model worst max-err/max {e_m:.2e} ({w_m}), norm rel {n_m:.2e}; ema {e_e:.2e} ({w_e}), "
           f"norm rel {n_e:.2e}")
     # Four Adam steps move every weight by up to 4e-3; fp32 summation-order differences (1e-6 relative) in a
     # gradient enter through m / (sqrt(v) + eps), which is scale free: the update of an element whose gradient is
     # ~1e-7 of the layer's can differ visibly.  Bound: 1e-3 of max|p| per tensor (a quarter of one step), norms 1e-4.
-    assert e_m <= 1e-3 and e_e <= 1e-3 and n_m <= 1e-4 and n_e <= 1e-4
+    # tf32x3: gradient differences are ~3e-5 relative instead of 1e-6: twice the element bound
+    lim = 1e-3 if math == "fp32" else 2e-3
+    assert e_m <= lim and e_e <= lim and n_m <= 1e-4 and n_e <= 1e-4
 
 
-@pytest.mark.parametrize("math", ["fp32", "tf32"])
+@pytest.mark.parametrize("math", ["fp32", "tf32", "tf32x3"])
 def test_full_sampling_chain_vs_oracle_cfg3(math):
     """BASELINE configs[2]: sample at scale 0 (100 steps) then sample_via_scale through scales 1-4 (52, 41, 31, 22
     steps) at balloons' sizes, B=1 -- 246 chained denoiser evaluations -- against the CPU oracle with the same noise
@@ -256,13 +265,14 @@ def test_full_sampling_chain_vs_oracle_cfg3(math):
     print(f"cfg-3 chain {math}: max abs error per scale {['%.2e' % e for e in errs]} on values in [-1, 1]")
     # measured (r02, B200): fp32 <= 2.7e-6, tf32 <= 2.3e-3 max abs on values in [-1, 1]; bounds ~ 2x measured (tf32) and
     # 4x (fp32: a handful of ulps after 246 chained evaluations)
-    bound = 1e-5 if math == "fp32" else 5e-3
+    # tf32x3: 3xTF32 per-convolution error is ~3e-6 instead of 1e-7; measured 5.1e-6, bound 4x that
+    bound = {"fp32": 1e-5, "tf32x3": 2e-5, "tf32": 5e-3}[math]
     assert max(errs) <= bound, errs
 
 
 @pytest.mark.parametrize("case", [("seascape finest (configs[3])", 200, 249, 3), ("starry_night x(2,2) finest (configs[4])", 396, 504, 4),
                                   ("starry_night x(2,2) coarsest", 98, 124, 0)])
-@pytest.mark.parametrize("math", ["fp32", "tf32"])
+@pytest.mark.parametrize("math", ["fp32", "tf32", "tf32x3"])
 def test_other_baseline_shapes_vs_oracle(case, math):
     """The denoiser at the image sizes of BASELINE configs[3] / configs[4] (not multiples of any tile size; 396x504 is
     4x the pixels of balloons' finest scale) against the CPU oracle, B = 2 with different timesteps per row."""
@@ -278,7 +288,7 @@ def test_other_baseline_shapes_vs_oracle(case, math):
         got = net(x.to(DEV), t.to(DEV), s).cpu()
     e_max, e_l2 = max_err_rel(got, ref), rel_err(got, ref)
     print(f"{case[0]} {math}: max-err/max {e_max:.2e}, rel L2 {e_l2:.2e}")
-    if math == "fp32":
+    if math in STRICT:
         assert e_max <= 2e-4
     else:
         assert e_max <= 3e-2 and e_l2 <= 5e-3
