@@ -18,6 +18,7 @@ not checkpoint optimizer state either (quirk Q12).
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional
 
 import torch
@@ -85,7 +86,6 @@ class FusedStep:
             # allocation has a multicast mapping and world >= 4 (no gain at 2); SINDDM_FUSED_MULTIMEM=0/1 overrides.
             # The summation order is then the switch's (NCCL's NVLS all-reduce agrees to 3e-8), not rank order; the
             # trainer's _check_replicas() guards the replicas at every milestone either way.
-            import os
             mc = int(getattr(self.handle, "multicast_ptr", 0) or 0)
             want = os.environ.get("SINDDM_FUSED_MULTIMEM", "")
             use = (want == "1") if want in ("0", "1") else self.world >= 4
