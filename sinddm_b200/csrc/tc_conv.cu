@@ -113,9 +113,30 @@ struct KernelArgs {
 constexpr int kTailBytes = (2 * kStagesA + 2 * kMaxStagesB + 2 * kMaxSlots + kEpiThreads / 32) * 8 + 16 +
                            (kMaxN + kMaxN * 3 + 4 + 128 * 3) * 4 + 64;
 
+// Epilogue flavours.  The epilogue block (`process`) holds every fused epilogue of the network behind run-time flags
+// and is unrolled five times for the drain-first register arrays: ~100 KB of code, of which one layer executes a
+// fraction, against a 32 KB L1.5 instruction cache (ncu: `no_instructions` was 10-22 % of the stall samples).  FL is a
+// compile-time mask of the features an instantiation MAY use: a feature whose bit is clear is compiled out, a feature
+// whose bit is set is still governed by its run-time flag, so any instantiation whose mask covers the layer's features
+// computes exactly what the generic one (kFlAll) does.  tc_conv_launch picks the smallest covering instantiation.
+enum : int {
+    kFlStream = 1,     // a streamed epilogue operand (res_add or dgelu_z) arrives through the per-warp TMA tile
+    kFlPre2 = 2,       // ... and a second one through plain loads (res_add AND dgelu_z: operator tests only)
+    kFlResAdd = 4,     // identity residual added
+    kFlDgelu = 8,      // multiply by gelu'(z) / the saved gelu'
+    kFlX3 = 16,        // 3-channel 1x1 residual conv as epilogue FMAs
+    kFlGelu = 32,      // GELU (and, with pre_grad, the saved gelu')
+    kFlPre = 64,       // pre-activation copy
+    kFlFinal = 128,    // fused trailing 1x1 conv to 3 channels
+    kFlOut3 = 256,     // [P,3] copy of columns 0..2
+    kFlColsum = 512,   // column sums of the stored tile
+    kFlRound = 1024,   // round the result to tf32
+    kFlAll = 2047
+};
+
 // TWO = true: CTA pairs (cluster of 2, cta_group::2): one M=256 MMA covers the same half of BOTH CTAs' tiles,
 // each CTA stages only half of the weight rows, and only the leader CTA issues MMAs.
-template <bool TWO>
+template <bool TWO, int FL>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_ares,
                const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_bres,
@@ -179,9 +200,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     if (warp >= kEpiWarp0) {
         const int t = threadIdx.x - kEpiWarp0 * 32;
         for (int i = t; i < N; i += kEpiThreads) s_bias[i] = a.ep.bias ? a.ep.bias[i] : 0.f;
-        if (a.ep.w_res3)
+        if ((FL & kFlX3) && a.ep.w_res3)
             for (int i = t; i < N * 3; i += kEpiThreads) s_wres3[i] = a.ep.w_res3[i];
-        if (a.ep.w_final) {
+        if ((FL & kFlFinal) && a.ep.w_final) {
             for (int i = t; i < N * 3; i += kEpiThreads) s_wfinal[i] = a.ep.w_final[i];
             if (t < 3) s_bfinal[t] = a.ep.b_final ? a.ep.b_final[t] : 0.f;
         }
@@ -411,7 +432,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             }
             umma_commit_elect(&tfull_bar[slot]);
         }
-      } else if (!TWO && a.issuers2 && a.l2pf && warp == 3 && (a.ep.res_add || a.ep.dgelu_z) && !(a.dbg & 2)) {
+      } else if (!TWO && (FL & kFlStream) && a.issuers2 && a.l2pf && warp == 3 && (a.ep.res_add || a.ep.dgelu_z) &&
+                 !(a.dbg & 2)) {
         // ------------------------------------------------------------ L2 prefetcher of the streamed epilogue operand
         // The epilogue warps stream the residual / saved pre-activation tile by tile with ONE box in flight per
         // warp (shared memory is spent on the operand rings), i.e. 16 KiB per SM against a DRAM latency of
@@ -559,8 +581,20 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         const uint32_t so2 = stg_u32 + lrow + ((2u ^ swz) << 4), so3 = stg_u32 + lrow + ((3u ^ swz) << 4);
         uint32_t in_phase = 0;
         int obuf = 0;
-        const float* gsrc = ep.res_add ? ep.res_add : ep.dgelu_z;   // streamed through TMA
-        const float* gsrc2 = (ep.res_add && ep.dgelu_z) ? ep.dgelu_z : nullptr;   // rare second stream: plain loads
+        // run-time epilogue flags, each gated by its compile-time flavour bit (see kFl*)
+        const bool e_resadd = (FL & kFlResAdd) ? ep.res_add != nullptr : false;
+        const bool e_dgelu = (FL & kFlDgelu) ? ep.dgelu_z != nullptr : false;
+        const bool e_x3 = (FL & kFlX3) ? ep.w_res3 != nullptr : false;
+        const bool e_gelu = (FL & kFlGelu) ? ep.gelu != 0 : false;
+        const bool e_pre = (FL & kFlPre) ? ep.out_pre != nullptr : false;
+        const bool e_final = (FL & kFlFinal) ? ep.w_final != nullptr : false;
+        const bool e_out3 = (FL & kFlOut3) ? ep.out3 != nullptr : false;
+        const bool e_colsum = (FL & kFlColsum) ? ep.colsum_part != nullptr : false;
+        const bool e_round = (FL & kFlRound) ? ep.round_tf32 != 0 : false;
+        const float* gsrc = (FL & kFlStream) ? (e_resadd ? ep.res_add : (e_dgelu ? ep.dgelu_z : nullptr))
+                                             : nullptr;   // streamed through TMA
+        const float* gsrc2 = (FL & kFlPre2) ? ((e_resadd && e_dgelu) ? ep.dgelu_z : nullptr)
+                                            : nullptr;    // rare second stream: plain loads
         uint32_t slot_uses[kMaxSlots] = {0, 0, 0, 0, 0};
         int titer = 0;
         // ep.colsum_part: column sums of everything this warp stores to `out` (its column share, its pixel quarter),
@@ -585,10 +619,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                 const int w0 = halo ? tw * 8 * a.nh + half * 8 : tw * kTileW;   // this warp's strip
                 const bool valid = live && (h < a.H) && (w < a.W);
                 const size_t pix = ((size_t)b * a.H + h) * a.W + w;
-                const unsigned vmask = ep.colsum_part ? __ballot_sync(0xffffffffu, valid) : 0u;
+                const unsigned vmask = e_colsum ? __ballot_sync(0xffffffffu, valid) : 0u;
 
                 float x3v[3] = {0.f, 0.f, 0.f};
-                if (ep.x3 && valid) {
+                if ((FL & kFlX3) && ep.x3 && valid) {
                     x3v[0] = ep.x3[pix * 3 + 0];
                     x3v[1] = ep.x3[pix * 3 + 1];
                     x3v[2] = ep.x3[pix * 3 + 2];
@@ -711,7 +745,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                             v[4 * q + 3] += bb.w;
                         }
                     }
-                    if (ep.w_res3) {
+                    if (e_x3) {
                         // the 16 columns' [3] weights are 48 consecutive floats (16-byte aligned: s_wres3 sits 976 B into
                         // the 1024-aligned tail, cc * 12 B is a multiple of 192): twelve broadcast LDS.128 through the
                         // shared window instead of 48 scalar loads through generic addresses
@@ -728,7 +762,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                             }
                         }
                     }
-                    if (ep.res_add) {
+                    if (e_resadd) {
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             v[4 * q + 0] += cur[q].x;
@@ -737,7 +771,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                             v[4 * q + 3] += cur[q].w;
                         }
                     }
-                    if (ep.gelu && ep.pre_grad && ep.out_pre) {
+                    if (e_gelu && ep.pre_grad && e_pre) {
                         // save gelu'(z) for the backward pass instead of z: cdf and pdf are both at hand here
                         float g[16];
 #pragma unroll
@@ -749,13 +783,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                         }
                         if (live) store_tile(&tm_pre, cc, g);
                     } else {
-                        if (ep.out_pre && live) store_tile(&tm_pre, cc, v);
-                        if (ep.gelu) {
+                        if (e_pre && live) store_tile(&tm_pre, cc, v);
+                        if (e_gelu) {
 #pragma unroll
                             for (int j = 0; j < 16; ++j) v[j] = gelu_fast(v[j]);
                         }
                     }
-                    if (ep.dgelu_z) {
+                    if (e_dgelu) {
                         const float4* z = gsrc2 ? pre2 : cur;
                         if (ep.pre_grad) {
 #pragma unroll
@@ -775,7 +809,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                             }
                         }
                     }
-                    if (ep.w_final) {
+                    if (e_final) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             fin[0] = fmaf(v[j], s_wfinal[0 * N + cc + j], fin[0]);
@@ -783,7 +817,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                             fin[2] = fmaf(v[j], s_wfinal[2 * N + cc + j], fin[2]);
                         }
                     }
-                    if (ep.out3 && cc == 0 && valid) {
+                    if (e_out3 && cc == 0 && valid) {
                         // a lane owns one pixel: the warp's 32 x 12 bytes are contiguous NHWC memory
                         float* o3 = ep.out3 + pix * 3;
                         o3[0] = v[0];
@@ -791,11 +825,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                         o3[2] = v[2];
                     }
                     if (ep.out && live) {
-                        if (ep.round_tf32) {
+                        if (e_round) {
 #pragma unroll
                             for (int j = 0; j < 16; ++j) v[j] = round_tf32(v[j]);
                         }
-                        store_tile(&tm_out, cc, v, ep.colsum_part ? &csum : nullptr);
+                        store_tile(&tm_out, cc, v, e_colsum ? &csum : nullptr);
                     }
                 };
                 {
@@ -820,7 +854,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                         if (cc + i * 2 * kEpiChunk < N) process(cc + i * 2 * kEpiChunk, r[i], csum_acc[i]);
                 }
 
-                if (ep.w_final) {
+                if (e_final) {
                     // the two column groups of a pixel combine their partial 3-channel sums through smem
                     if (cgrp == 1) {
                         s_fin[row * 3 + 0] = fin[0];
@@ -841,7 +875,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         }
         if (lane == 0) bulk_wait_group_read<0>();   // the staging tiles are read until the last store has drained
         __syncwarp();
-        if (ep.colsum_part && lane < 16) {
+        if (e_colsum && lane < 16) {
             float* dst = ep.colsum_part + ((size_t)blockIdx.x * 4 + quarter) * N + cgrp * kEpiChunk + lane;
 #pragma unroll
             for (int i = 0; i < kMaxN / (2 * kEpiChunk); ++i)
@@ -858,6 +892,46 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         if (TWO) tmem_dealloc_2sm(tmem_base, kTmemCols);
         else tmem_dealloc(tmem_base, kTmemCols);
     }
+}
+
+// The instantiations, most specific first (tc_conv_launch takes the first whose mask covers the layer).  The masks are
+// the epilogues SinDDMNet's plan uses (net.cu); anything else -- operator tests, future layers -- runs the generic one.
+using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                          const CUtensorMap, const CUtensorMap, const KernelArgs);
+struct Flavour {
+    int mask;
+    KernelFn fn;
+    const char* what;
+};
+constexpr int kFlC1 = kFlGelu | kFlPre | kFlRound;                       // net[0]: GELU (+ saved gelu' when training)
+constexpr int kFlRes = kFlStream | kFlResAdd;                            // l3.net[2]: + identity residual (streamed)
+constexpr int kFlD2 = kFlStream | kFlDgelu | kFlColsum | kFlRound;       // data gradient through GELU + column sums
+const Flavour kFlavours[] = {
+    {0, tc_conv_kernel<false, 0>, "plain (bias only): residual-slice layers, first-conv / residual data gradients"},
+    {kFlOut3, tc_conv_kernel<false, kFlOut3>, "3-channel data gradient (N padded to 16)"},
+    {kFlX3, tc_conv_kernel<false, kFlX3>, "l1.net[2]: 3-channel residual conv in the epilogue"},
+    {kFlFinal, tc_conv_kernel<false, kFlFinal>, "l4.net[2]: fused final 1x1 conv"},
+    {kFlRes, tc_conv_kernel<false, kFlRes>, "l3.net[2]: streamed identity residual"},
+    {kFlC1, tc_conv_kernel<false, kFlC1>, "net[0]: GELU, saved gelu', tf32 rounding"},
+    {kFlD2, tc_conv_kernel<false, kFlD2>, "net[2] data gradient: streamed gelu', column sums, tf32 rounding"},
+    {kFlAll, tc_conv_kernel<false, kFlAll>, "generic"},
+};
+constexpr int kNumFlavours = (int)(sizeof(kFlavours) / sizeof(kFlavours[0]));
+
+int flavour_need(const ConvEpilogue& ep) {
+    int need = 0;
+    if (ep.res_add || ep.dgelu_z) need |= kFlStream;
+    if (ep.res_add && ep.dgelu_z) need |= kFlPre2;
+    if (ep.res_add) need |= kFlResAdd;
+    if (ep.dgelu_z) need |= kFlDgelu;
+    if (ep.x3 || ep.w_res3) need |= kFlX3;
+    if (ep.gelu) need |= kFlGelu;
+    if (ep.out_pre) need |= kFlPre;
+    if (ep.w_final) need |= kFlFinal;
+    if (ep.out3) need |= kFlOut3;
+    if (ep.colsum_part) need |= kFlColsum;
+    if (ep.round_tf32) need |= kFlRound;
+    return need;
 }
 
 }  // namespace
@@ -977,13 +1051,30 @@ int tc_conv_prepare(const ConvProblem& p, TcConvOp* op) {
 int tc_conv_launch(const TcConvOp& op, cudaStream_t stream) {
     // opt-in shared memory size: set once per process (function-local static: thread-safe initialisation)
     static const cudaError_t smem_set = []() {
-        cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             device_info().max_smem_optin);
-        if (e != cudaSuccess) return e;
-        return cudaFuncSetAttribute(tc_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        for (int i = 0; i < kNumFlavours; ++i) {
+            cudaError_t e = cudaFuncSetAttribute(kFlavours[i].fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 device_info().max_smem_optin);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaFuncSetAttribute(tc_conv_kernel<true, kFlAll>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     device_info().max_smem_optin);
     }();
     SINDDM_CUDA_OK(smem_set);
+    // the smallest instantiation whose compile-time flavour mask covers this launch's epilogue (SINDDM_TC_FLAVOURS=0:
+    // always the generic one -- A/B switch and the reference the specialised ones are tested against)
+    static const bool use_flavours = []() {
+        const char* e = getenv("SINDDM_TC_FLAVOURS");
+        return !(e && atoi(e) == 0);
+    }();
+    KernelFn kernel = kFlavours[kNumFlavours - 1].fn;
+    if (use_flavours) {
+        const int need = flavour_need(op.p.ep);
+        for (int i = 0; i < kNumFlavours; ++i)
+            if ((need & ~kFlavours[i].mask) == 0) {
+                kernel = kFlavours[i].fn;
+                break;
+            }
+    }
     const ConvProblem& p = op.p;
     KernelArgs a;
     a.B = p.B;
@@ -1033,7 +1124,7 @@ int tc_conv_launch(const TcConvOp& op, cudaStream_t stream) {
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        cudaError_t lerr = cudaLaunchKernelEx(&cfg, tc_conv_kernel<true>, op.tm_a, op.tm_ares, op.tm_b, op.tm_bres,
+        cudaError_t lerr = cudaLaunchKernelEx(&cfg, tc_conv_kernel<true, kFlAll>, op.tm_a, op.tm_ares, op.tm_b, op.tm_bres,
                                               op.tm_out, op.tm_pre, op.tm_in, a);
         if (lerr != cudaSuccess) {
             prof_end(stream);
@@ -1041,7 +1132,7 @@ int tc_conv_launch(const TcConvOp& op, cudaStream_t stream) {
             return SINDDM_ERR_CUDA;
         }
     } else {
-        (void)launch_pdl(tc_conv_kernel<false>, dim3(op.grid), dim3(kThreads), (size_t)op.smem_bytes, stream, op.tm_a,
+        (void)launch_pdl(kernel, dim3(op.grid), dim3(kThreads), (size_t)op.smem_bytes, stream, op.tm_a,
                          op.tm_ares, op.tm_b, op.tm_bres, op.tm_out, op.tm_pre, op.tm_in, a);
     }
     prof_end(stream);
