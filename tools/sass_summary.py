@@ -16,6 +16,7 @@ for line in out.splitlines():
     m = re.search(r"Function : (\S+)", line)
     if m:
         kern = subprocess.run(["cu++filt", m.group(1)], capture_output=True, text=True).stdout.strip()
+        kern = re.sub(r"\((?:bool|int)\)", "", kern)            # template arguments print as (bool)0, (int)1120
         kern = re.sub(r"\(.*", "", kern).replace("sinddm::", "").replace("(anonymous namespace)::", "").replace("void ", "")
         counts[kern] = collections.Counter()
         continue
