@@ -68,3 +68,26 @@ def test_product_never_imports_the_oracle():
         if py.exists():
             src = py.read_text()
             assert "oracle" not in src, py
+
+
+def test_math_modes_agree_between_header_binding_and_cli(monkeypatch):
+    """SINDDM_MATH_* in the header == the ctypes constants == what `--math` / SINDDM_MATH select; a tf32x3 plan needs
+    the split-operand buffers and the tripled weight operands on top of the TF32 plan's workspace."""
+    import main as cli
+    from sinddm_b200 import _capi, denoiser
+    text = HEADER.read_text()
+    m = re.search(r"enum \{ SINDDM_MATH_FP32 = (\d+), SINDDM_MATH_TF32 = (\d+), SINDDM_MATH_TF32X3 = (\d+) \};", text)
+    assert m, "math-mode enum not found in the header"
+    assert tuple(int(v) for v in m.groups()) == (_capi.MATH_FP32, _capi.MATH_TF32, _capi.MATH_TF32X3) == (0, 1, 2)
+    for name, val in (("fp32", 0), ("tf32", 1), ("tf32x3", 2)):
+        monkeypatch.setenv("SINDDM_MATH", name)
+        assert denoiser.default_math() == val
+        assert cli.build_parser().parse_args(["--math", name]).math == name
+    monkeypatch.delenv("SINDDM_MATH")
+    assert denoiser.default_math() == _capi.MATH_TF32          # the reference's own GPU default (cudnn.allow_tf32)
+    lib = _capi.load()
+    B, H, W, dim = 4, 94, 126, 160
+    tf32 = lib.sinddm_plan_workspace_bytes(B, H, W, dim, 3, _capi.MATH_TF32, 1)
+    x3 = lib.sinddm_plan_workspace_bytes(B, H, W, dim, 3, _capi.MATH_TF32X3, 1)
+    split = 2 * 3 * B * H * W * dim * 4                          # split_a + split_b
+    assert split <= x3 - tf32 <= split + 64 * 2**20              # + the [lo | hi | hi] weight operands (a few MB)
