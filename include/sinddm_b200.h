@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SINDDM_ABI_VERSION 2
+#define SINDDM_ABI_VERSION 3
 
 typedef enum sinddm_status {
     SINDDM_STATUS_OK = 0,

@@ -129,7 +129,7 @@ def load():
             fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
             fn.restype = res
             fn.argtypes = args
-        if lib.sinddm_abi_version() != 2:
+        if lib.sinddm_abi_version() != 3:
             raise SinddmError("libsinddm_b200.so ABI version mismatch")
         _lib = lib
     return _lib

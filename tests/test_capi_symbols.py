@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
         assert name in _capi.SIGNATURES, f"{name} has no ctypes signature"
     assert sorted(_capi.SIGNATURES) == declared_functions()
-    assert lib.sinddm_abi_version() == 2
+    assert lib.sinddm_abi_version() == 3
 
 
 def test_workspace_queries_run_without_a_gpu():
