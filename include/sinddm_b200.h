@@ -124,6 +124,14 @@ typedef struct sinddm_conv_desc {
 } sinddm_conv_desc;
 int sinddm_conv_forward(const sinddm_conv_desc* desc, int math, void* stream);
 
+/* Host-only query (no GPU needed): the tensor-core kernel is compiled once per set of epilogue features ("flavour": a
+ * bit mask -- 1 streamed operand, 2 second streamed operand, 4 identity residual, 8 gelu' multiply, 16 3-channel
+ * residual, 32 GELU, 64 pre-activation copy, 128 final conv, 256 3-channel copy, 512 column sums, 1024 tf32 rounding)
+ * and a launch runs the smallest instantiation covering the descriptor's epilogue.  Returns that instantiation's mask
+ * (2047 = the generic one), or a negative status.  Same numerics whichever runs; this exists so tests and profiles
+ * can name the kernel (`tc_conv_kernel<0, mask>` in ncu). */
+int sinddm_conv_epilogue_flavour(const sinddm_conv_desc* desc);
+
 /* PyTorch OIHW weight [Cout][Cin][ntaps] -> forward operand dst_fwd[tap][Cout][Cin] and/or data-gradient
  * operand dst_dgrad[tap][Cin][Cout] (taps flipped). Either destination may be NULL.
  * round_tf32: 0 = as is, 1 = rounded to TF32, 2 = the 3xTF32 split: the contraction axis is tripled as

@@ -83,6 +83,7 @@ SIGNATURES = {
     "sinddm_net_forward": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp]),
     "sinddm_net_backward": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "sinddm_conv_forward": (_i, [C.POINTER(ConvDesc), _i, _vp]),
+    "sinddm_conv_epilogue_flavour": (_i, [C.POINTER(ConvDesc)]),
     "sinddm_pack_conv_weights": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp]),
     "sinddm_split3": (_i, [_vp, _ll, _i, _vp, _i, _vp]),
     "sinddm_conv_wgrad_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i]),

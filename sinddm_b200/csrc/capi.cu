@@ -74,11 +74,8 @@ int sinddm_net_backward(sinddm_plan* plan, const float* const* params, const flo
     return net_backward(&plan->p, params, dout, grads, as_stream(stream));
 }
 
-int sinddm_conv_forward(const sinddm_conv_desc* d, int math, void* stream) {
-    SINDDM_REQUIRE(d != nullptr, "conv_forward: NULL descriptor");
-    SINDDM_REQUIRE(d->in && d->w, "conv_forward: in / w are required");
-    SINDDM_REQUIRE(d->out || d->out_final, "conv_forward: no output requested");
-    ConvProblem p;
+static void conv_problem_from_desc(const sinddm_conv_desc* d, ConvProblem* out) {
+    ConvProblem& p = *out;
     memset(&p, 0, sizeof(p));
     p.B = d->B; p.H = d->H; p.W = d->W;
     p.in = d->in; p.Cin = d->Cin; p.w = d->w; p.ntaps = d->ntaps;
@@ -88,6 +85,21 @@ int sinddm_conv_forward(const sinddm_conv_desc* d, int math, void* stream) {
     p.ep.gelu = d->gelu; p.ep.out_pre = d->out_pre; p.ep.dgelu_z = d->dgelu_z;
     p.ep.w_final = d->w_final; p.ep.b_final = d->b_final; p.ep.out_final = d->out_final;
     p.ep.round_tf32 = d->round_tf32; p.ep.out = d->out; p.ep.out3 = nullptr; p.ep.pre_grad = 0; p.ep.fast_math = 0;
+}
+
+int sinddm_conv_epilogue_flavour(const sinddm_conv_desc* d) {
+    SINDDM_REQUIRE(d != nullptr, "conv_epilogue_flavour: NULL descriptor");
+    ConvProblem p;
+    conv_problem_from_desc(d, &p);
+    return tc_conv_flavour_mask(p.ep);
+}
+
+int sinddm_conv_forward(const sinddm_conv_desc* d, int math, void* stream) {
+    SINDDM_REQUIRE(d != nullptr, "conv_forward: NULL descriptor");
+    SINDDM_REQUIRE(d->in && d->w, "conv_forward: in / w are required");
+    SINDDM_REQUIRE(d->out || d->out_final, "conv_forward: no output requested");
+    ConvProblem p;
+    conv_problem_from_desc(d, &p);
     SINDDM_REQUIRE(p.B >= 1 && p.H >= 1 && p.W >= 1 && p.Cin >= 1 && p.N >= 1, "conv_forward: bad shape");
     SINDDM_REQUIRE(!p.ep.x3 || p.ep.w_res3, "conv_forward: x3 given without w_res3");
     SINDDM_REQUIRE(!p.ep.w_final || p.ep.out_final, "conv_forward: w_final given without out_final");

@@ -77,6 +77,9 @@ int colsum_final_launch(const float* part, int nrows, int C, float* out, cudaStr
 bool tc_conv_supported(const ConvProblem& p);
 int tc_conv_prepare(const ConvProblem& p, TcConvOp* op);
 int tc_conv_launch(const TcConvOp& op, cudaStream_t stream);
+// compile-time epilogue-feature mask of the tc_conv_kernel instantiation a launch with this epilogue runs
+// (tc_conv.cu: kFl*; 2047 = the generic instantiation)
+int tc_conv_flavour_mask(const ConvEpilogue& ep);
 
 int simt_conv_launch(const ConvProblem& p, cudaStream_t stream);
 

@@ -936,6 +936,14 @@ int flavour_need(const ConvEpilogue& ep) {
 
 }  // namespace
 
+// Flavour mask of the instantiation tc_conv_launch picks for this epilogue (kFlAll = the generic one).
+int tc_conv_flavour_mask(const ConvEpilogue& ep) {
+    const int need = flavour_need(ep);
+    for (int i = 0; i < kNumFlavours; ++i)
+        if ((need & ~kFlavours[i].mask) == 0) return kFlavours[i].mask;
+    return kFlAll;
+}
+
 static int two_sm_setting() {
     static int v = -1;
     if (v < 0) {

@@ -91,3 +91,32 @@ def test_math_modes_agree_between_header_binding_and_cli(monkeypatch):
     x3 = lib.sinddm_plan_workspace_bytes(B, H, W, dim, 3, _capi.MATH_TF32X3, 1)
     split = 2 * 3 * B * H * W * dim * 4                          # split_a + split_b
     assert split <= x3 - tf32 <= split + 64 * 2**20              # + the [lo | hi | hi] weight operands (a few MB)
+
+
+def test_conv_launch_picks_the_smallest_covering_epilogue_flavour():
+    """tc_conv_kernel is instantiated per set of epilogue features; the launch picks the smallest instantiation that
+    covers the descriptor (host-only query, no GPU).  The masks are the ones ncu shows in the kernel names."""
+    from sinddm_b200 import _capi
+    lib = _capi.load()
+    P = 0x1000      # any non-NULL address: the query never dereferences
+
+    def flavour(**kw):
+        d = _capi.ConvDesc()
+        d.B, d.H, d.W, d.Cin, d.N, d.ntaps = 1, 8, 8, 80, 80, 9
+        d.inp, d.w, d.out = P, P, P
+        for k, v in kw.items():
+            setattr(d, k, v)
+        return lib.sinddm_conv_epilogue_flavour(ctypes.byref(d))
+
+    STREAM, PRE2, RESADD, DGELU, X3, GELU, PRE, FINAL, OUT3, COLSUM, ROUND = (1 << i for i in range(11))
+    assert flavour() == 0                                                   # residual-slice layers, plain data gradients
+    assert flavour(bias=P) == 0
+    assert flavour(gelu=1) == flavour(gelu=1, out_pre=P, round_tf32=1) == GELU | PRE | ROUND          # net[0]
+    assert flavour(x3=P, w_res3=P) == X3                                    # l1.net[2]
+    assert flavour(res_add=P) == STREAM | RESADD                            # l3.net[2]
+    assert flavour(w_final=P, b_final=P, out_final=P) == FINAL              # l4.net[2]
+    assert flavour(dgelu_z=P, round_tf32=1) == STREAM | DGELU | COLSUM | ROUND      # net[2] data gradient
+    assert flavour(round_tf32=1) == GELU | PRE | ROUND                      # smallest instantiation that can round
+    assert flavour(res_add=P, dgelu_z=P) == 2047                            # two streamed operands: only the generic one
+    assert flavour(gelu=1, res_add=P) == 2047
+    assert lib.sinddm_conv_epilogue_flavour(None) < 0
